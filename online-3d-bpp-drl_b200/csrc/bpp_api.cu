@@ -1,0 +1,389 @@
+// bpp_api.cu -- the C ABI of libbpp_b200.so (include/bpp_b200.h).  Host-side plumbing only: argument
+// validation, device memory owned by the env, launches.  No CPU fallback exists: without a usable
+// sm_100 device every entry point fails with BPP_ERR_NO_DEVICE / BPP_ERR_CUDA.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/bpp_b200.h"
+#include "bpp_launch.h"
+
+using namespace bpp;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define BPP_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(BPP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int device_grid_cap(int device, int *num_sms)
+{
+    cudaDeviceProp prop;
+    BPP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(BPP_ERR_NO_DEVICE, "libbpp_b200 is built for sm_100a only; device " + std::to_string(device) +
+                                           " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+    *num_sms = prop.multiProcessorCount;
+    return BPP_OK;
+}
+
+}  // namespace
+
+struct bpp_env {
+    bpp_config cfg;
+    EnvParams p;
+    int rot, variant;
+    int num_sms, blocks_per_sm[2];   // [vec4]
+    size_t smem;
+    bool was_reset;
+    unsigned long long steps;
+    // device memory owned by the env
+    uint8_t *d_hm;
+    BinScalars *d_sc;
+    uint32_t *d_items, *d_traj, *d_ep_items;
+    int32_t *d_traj_len;
+    unsigned long long *d_metrics;
+    // staging for the host-buffer entry point
+    long long *d_actions;
+    float *d_reward, *d_ratio;
+    uint8_t *d_done;
+    int32_t *d_counter;
+};
+
+extern "C" {
+
+int32_t bpp_abi_version(void) { return BPP_ABI_VERSION; }
+const char *bpp_last_error(void) { return g_last_error.c_str(); }
+uint64_t bpp_launch_count(void) { return g_launches.load(); }
+
+int32_t bpp_destroy(bpp_env *env)
+{
+    if (!env) return BPP_OK;
+    cudaSetDevice(env->cfg.device);
+    cudaFree(env->d_hm); cudaFree(env->d_sc); cudaFree(env->d_items); cudaFree(env->d_traj);
+    cudaFree(env->d_ep_items); cudaFree(env->d_traj_len); cudaFree(env->d_metrics); cudaFree(env->d_actions);
+    cudaFree(env->d_reward); cudaFree(env->d_ratio); cudaFree(env->d_done); cudaFree(env->d_counter);
+    delete env;
+    return BPP_OK;
+}
+
+int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
+{
+    if (!cfg || !out) return fail(BPP_ERR_INVALID, "bpp_create: null argument");
+    *out = nullptr;
+    if (cfg->abi_version != BPP_ABI_VERSION) return fail(BPP_ERR_INVALID, "bpp_create: ABI version mismatch");
+    if (cfg->n_bins <= 0) return fail(BPP_ERR_INVALID, "bpp_create: n_bins must be positive");
+    if (cfg->L < 1 || cfg->W < 1 || cfg->L > kMaxSide || cfg->W > kMaxSide)
+        return fail(BPP_ERR_INVALID, "bpp_create: L and W must be in [1, 32]");
+    if (cfg->H < 1 || cfg->H > 255) return fail(BPP_ERR_INVALID, "bpp_create: H must be in [1, 255]");
+    if (cfg->mask_variant != BPP_MASK_V1 && cfg->mask_variant != BPP_MASK_V2)
+        return fail(BPP_ERR_INVALID, "bpp_create: mask_variant must be 1 or 2");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
+        return fail(BPP_ERR_NO_DEVICE, "bpp_create: no CUDA device (this library has no CPU path)");
+    if (cfg->device < 0 || cfg->device >= count) return fail(BPP_ERR_INVALID, "bpp_create: bad device ordinal");
+    int num_sms = 0;
+    if (int rc = device_grid_cap(cfg->device, &num_sms)) return rc;
+    BPP_CUDA(cudaSetDevice(cfg->device));
+
+    bpp_env *e = new (std::nothrow) bpp_env();
+    if (!e) return fail(BPP_ERR_INVALID, "bpp_create: out of host memory");
+    std::memset(static_cast<void *>(e), 0, sizeof(*e));
+    e->cfg = *cfg;
+    e->rot = cfg->rot ? 1 : 0;
+    e->variant = cfg->mask_variant;
+    e->num_sms = num_sms;
+    EnvParams &p = e->p;
+    p.N = cfg->n_bins; p.L = cfg->L; p.W = cfg->W; p.H = cfg->H;
+    p.A = cfg->L * cfg->W; p.A_pad = (p.A + 15) & ~15;
+    p.M = p.A * (e->rot ? 2 : 1); p.M_pad = (p.M + 15) & ~15;
+    p.gen_kind = cfg->gen_kind;
+    p.seed_lo = (uint32_t)cfg->seed; p.seed_hi = (uint32_t)(cfg->seed >> 32);
+    p.global_offset = (unsigned long long)cfg->global_offset;
+    p.lwh = (double)cfg->L * (double)cfg->W * (double)cfg->H;
+    const long long global_n = cfg->global_n > 0 ? cfg->global_n : cfg->n_bins;
+
+#define BPP_CREATE_CUDA(expr)                                                                       \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            std::string m = std::string(#expr) + ": " + cudaGetErrorString(_e);                     \
+            bpp_destroy(e);                                                                         \
+            return fail(BPP_ERR_CUDA, m);                                                           \
+        }                                                                                           \
+    } while (0)
+
+    switch (cfg->gen_kind) {
+    case BPP_GEN_RS: {
+        if (cfg->n_items <= 0 || !cfg->item_set_host) { bpp_destroy(e); return fail(BPP_ERR_INVALID, "bpp_create: rs needs an item set"); }
+        std::vector<uint32_t> packed((size_t)cfg->n_items);
+        for (int i = 0; i < cfg->n_items; ++i) {
+            const uint8_t *it = cfg->item_set_host + (size_t)i * 3;
+            if (!it[0] || !it[1] || !it[2]) { bpp_destroy(e); return fail(BPP_ERR_INVALID, "bpp_create: item dims must be >= 1"); }
+            packed[i] = it[0] | (it[1] << 8) | (it[2] << 16);
+        }
+        BPP_CREATE_CUDA(cudaMalloc(&e->d_items, packed.size() * 4));
+        BPP_CREATE_CUDA(cudaMemcpy(e->d_items, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+        p.n_items = cfg->n_items; p.item_set = e->d_items;
+        break;
+    }
+    case BPP_GEN_REPLAY: {
+        if (cfg->n_traj <= 0 || cfg->traj_cap <= 0 || !cfg->traj_host || !cfg->traj_len_host) {
+            bpp_destroy(e); return fail(BPP_ERR_INVALID, "bpp_create: replay needs trajectories");
+        }
+        const size_t rows = (size_t)cfg->n_traj, cap = (size_t)cfg->traj_cap;
+        std::vector<uint32_t> packed(rows * cap, 0u);
+        for (size_t t = 0; t < rows; ++t) {
+            if (cfg->traj_len_host[t] < 0 || cfg->traj_len_host[t] > cfg->traj_cap) {
+                bpp_destroy(e); return fail(BPP_ERR_INVALID, "bpp_create: traj_len out of range");
+            }
+            for (int k = 0; k < cfg->traj_len_host[t]; ++k) {
+                const uint8_t *it = cfg->traj_host + (t * cap + k) * 3;
+                if (!it[0] || !it[1] || !it[2]) { bpp_destroy(e); return fail(BPP_ERR_INVALID, "bpp_create: item dims must be >= 1"); }
+                packed[t * cap + k] = it[0] | (it[1] << 8) | (it[2] << 16);
+            }
+        }
+        BPP_CREATE_CUDA(cudaMalloc(&e->d_traj, packed.size() * 4));
+        BPP_CREATE_CUDA(cudaMemcpy(e->d_traj, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+        BPP_CREATE_CUDA(cudaMalloc(&e->d_traj_len, rows * 4));
+        BPP_CREATE_CUDA(cudaMemcpy(e->d_traj_len, cfg->traj_len_host, rows * 4, cudaMemcpyHostToDevice));
+        p.n_traj = cfg->n_traj; p.traj_cap = cfg->traj_cap; p.traj = e->d_traj; p.traj_len = e->d_traj_len;
+        const long long T = cfg->n_traj;
+        p.first_mod = (uint32_t)(((cfg->first_traj % T) + T) % T);
+        p.gn_mod = (uint32_t)(global_n % T);
+        break;
+    }
+    default:
+        bpp_destroy(e);
+        return fail(BPP_ERR_INVALID, "bpp_create: generator kind not available in this build (rs and replay are)");
+    }
+
+    const size_t N = (size_t)p.N;
+    BPP_CREATE_CUDA(cudaMalloc(&e->d_hm, N * p.A_pad));
+    BPP_CREATE_CUDA(cudaMemset(e->d_hm, 0, N * p.A_pad));
+    BPP_CREATE_CUDA(cudaMalloc(&e->d_sc, N * sizeof(BinScalars)));
+    BPP_CREATE_CUDA(cudaMemset(e->d_sc, 0, N * sizeof(BinScalars)));
+    BPP_CREATE_CUDA(cudaMalloc(&e->d_metrics, 4 * sizeof(unsigned long long)));
+    BPP_CREATE_CUDA(cudaMemset(e->d_metrics, 0, 4 * sizeof(unsigned long long)));
+    BPP_CREATE_CUDA(cudaMalloc(&e->d_actions, N * sizeof(long long)));
+    BPP_CREATE_CUDA(cudaMalloc(&e->d_reward, N * sizeof(float)));
+    BPP_CREATE_CUDA(cudaMalloc(&e->d_ratio, N * sizeof(float)));
+    BPP_CREATE_CUDA(cudaMalloc(&e->d_done, N));
+    BPP_CREATE_CUDA(cudaMalloc(&e->d_counter, N * sizeof(int32_t)));
+    p.hm = e->d_hm; p.sc = e->d_sc; p.metrics = e->d_metrics;
+
+    e->smem = (size_t)kWarpsPerBlock * (p.A_pad + p.M_pad);
+    for (int v = 0; v < 2; ++v) {
+        int b = 0;
+        BPP_CREATE_CUDA(step_occupancy(e->rot, e->variant, v == 1, e->smem, &b));
+        e->blocks_per_sm[v] = b > 0 ? b : 1;
+    }
+    *out = e;
+    return BPP_OK;
+}
+
+static int run_step(bpp_env *env, const StepIO &io, int mode, void *stream)
+{
+    const EnvParams &p = env->p;
+    const bool vec4 = (p.A % 4 == 0) && (!io.obs || aligned16(io.obs)) && (!io.mask || aligned16(io.mask));
+    // persistent CTAs: one wave of resident blocks, grid-stride over bins
+    const long long want = ((long long)p.N + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const long long cap = (long long)env->num_sms * env->blocks_per_sm[vec4 ? 1 : 0];
+    const int grid = (int)(want < cap ? want : cap);
+    BPP_CUDA(launch_step(p, io, mode, env->rot, env->variant, vec4, grid, env->smem, as_stream(stream)));
+    g_launches.fetch_add(1);
+    return BPP_OK;
+}
+
+static int enter(bpp_env *env, const char *who)
+{
+    if (!env) return fail(BPP_ERR_INVALID, std::string(who) + ": null env");
+    BPP_CUDA(cudaSetDevice(env->cfg.device));
+    return BPP_OK;
+}
+
+int32_t bpp_reset(bpp_env *env, float *obs, float *mask, int64_t *sample, void *stream)
+{
+    if (int rc = enter(env, "bpp_reset")) return rc;
+    StepIO io{};
+    io.obs = obs; io.mask = mask; io.sample = reinterpret_cast<long long *>(sample);
+    io.episode_inc = env->was_reset ? 1 : 0;
+    if (int rc = run_step(env, io, kModeReset, stream)) return rc;
+    env->was_reset = true;
+    return BPP_OK;
+}
+
+int32_t bpp_step(bpp_env *env, const int64_t *actions, float *obs, float *mask, float *reward, uint8_t *done,
+                 int32_t *counter, float *ratio, int64_t *sample, void *stream)
+{
+    if (int rc = enter(env, "bpp_step")) return rc;
+    if (!env->was_reset) return fail(BPP_ERR_STATE, "bpp_step: call bpp_reset first");
+    if (!actions) return fail(BPP_ERR_INVALID, "bpp_step: actions is null");
+    StepIO io{};
+    io.actions = reinterpret_cast<const long long *>(actions);
+    io.obs = obs; io.mask = mask; io.reward = reward; io.done = done; io.counter = counter; io.ratio = ratio;
+    io.sample = reinterpret_cast<long long *>(sample);
+    if (int rc = run_step(env, io, kModeStep, stream)) return rc;
+    env->steps += (unsigned long long)env->p.N;
+    return BPP_OK;
+}
+
+int32_t bpp_step_host(bpp_env *env, const int64_t *actions_host, float *obs, float *mask, float *reward_host,
+                      uint8_t *done_host, int32_t *counter_host, float *ratio_host, int64_t *sample, void *stream)
+{
+    if (int rc = enter(env, "bpp_step_host")) return rc;
+    if (!env->was_reset) return fail(BPP_ERR_STATE, "bpp_step_host: call bpp_reset first");
+    if (!actions_host) return fail(BPP_ERR_INVALID, "bpp_step_host: actions_host is null");
+    cudaStream_t st = as_stream(stream);
+    const size_t N = (size_t)env->p.N;
+    BPP_CUDA(cudaMemcpyAsync(env->d_actions, actions_host, N * sizeof(long long), cudaMemcpyHostToDevice, st));
+    StepIO io{};
+    io.actions = env->d_actions;
+    io.obs = obs; io.mask = mask;
+    io.reward = reward_host ? env->d_reward : nullptr;
+    io.done = done_host ? env->d_done : nullptr;
+    io.counter = counter_host ? env->d_counter : nullptr;
+    io.ratio = ratio_host ? env->d_ratio : nullptr;
+    io.sample = reinterpret_cast<long long *>(sample);
+    if (int rc = run_step(env, io, kModeStep, stream)) return rc;
+    env->steps += (unsigned long long)N;
+    if (reward_host) BPP_CUDA(cudaMemcpyAsync(reward_host, env->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (done_host) BPP_CUDA(cudaMemcpyAsync(done_host, env->d_done, N, cudaMemcpyDeviceToHost, st));
+    if (counter_host) BPP_CUDA(cudaMemcpyAsync(counter_host, env->d_counter, N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (ratio_host) BPP_CUDA(cudaMemcpyAsync(ratio_host, env->d_ratio, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    BPP_CUDA(cudaStreamSynchronize(st));
+    return BPP_OK;
+}
+
+int32_t bpp_observe(bpp_env *env, float *obs, float *mask, void *stream)
+{
+    if (int rc = enter(env, "bpp_observe")) return rc;
+    if (!env->was_reset) return fail(BPP_ERR_STATE, "bpp_observe: call bpp_reset first");
+    StepIO io{};
+    io.obs = obs; io.mask = mask;
+    return run_step(env, io, kModeObserve, stream);
+}
+
+static int stateless_grid(int n, int *grid)
+{
+    int dev = 0, sms = 0;
+    BPP_CUDA(cudaGetDevice(&dev));
+    if (int rc = device_grid_cap(dev, &sms)) return rc;
+    const long long want = ((long long)n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const long long cap = (long long)sms * 8;
+    *grid = (int)(want < cap ? want : cap);
+    return BPP_OK;
+}
+
+static int check_dims(const char *who, int n, int L, int W, int H, int variant)
+{
+    if (n < 0) return fail(BPP_ERR_INVALID, std::string(who) + ": negative n");
+    if (L < 1 || W < 1 || L > kMaxSide || W > kMaxSide) return fail(BPP_ERR_INVALID, std::string(who) + ": L and W must be in [1, 32]");
+    if (H < 1 || H > 255) return fail(BPP_ERR_INVALID, std::string(who) + ": H must be in [1, 255]");
+    if (variant != 1 && variant != 2) return fail(BPP_ERR_INVALID, std::string(who) + ": variant must be 1 or 2");
+    return BPP_OK;
+}
+
+int32_t bpp_mask_from_obs(const float *obs, int32_t n, int32_t L, int32_t W, int32_t H, int32_t rot, int32_t variant,
+                          float *mask, void *stream)
+{
+    if (int rc = check_dims("bpp_mask_from_obs", n, L, W, H, variant)) return rc;
+    if (n == 0) return BPP_OK;
+    if (!obs || !mask) return fail(BPP_ERR_INVALID, "bpp_mask_from_obs: null pointer");
+    int grid = 0;
+    if (int rc = stateless_grid(n, &grid)) return rc;
+    BPP_CUDA(launch_mask_from_obs(obs, n, L, W, H, rot ? 1 : 0, variant, mask, grid, as_stream(stream)));
+    g_launches.fetch_add(1);
+    return BPP_OK;
+}
+
+int32_t bpp_mask_from_plain(const int32_t *plain, const int32_t *box, int32_t n, int32_t L, int32_t W, int32_t H,
+                            int32_t rot, int32_t variant, float *mask, void *stream)
+{
+    if (int rc = check_dims("bpp_mask_from_plain", n, L, W, H, variant)) return rc;
+    if (n == 0) return BPP_OK;
+    if (!plain || !box || !mask) return fail(BPP_ERR_INVALID, "bpp_mask_from_plain: null pointer");
+    int grid = 0;
+    if (int rc = stateless_grid(n, &grid)) return rc;
+    BPP_CUDA(launch_mask_from_plain(plain, box, n, L, W, H, rot ? 1 : 0, variant, mask, grid, as_stream(stream)));
+    g_launches.fetch_add(1);
+    return BPP_OK;
+}
+
+int32_t bpp_check_box(const int32_t *plain, const int32_t *query, int32_t n, int32_t L, int32_t W, int32_t H,
+                      int32_t variant, int32_t *out, void *stream)
+{
+    if (int rc = check_dims("bpp_check_box", n, L, W, H, variant)) return rc;
+    if (n == 0) return BPP_OK;
+    if (!plain || !query || !out) return fail(BPP_ERR_INVALID, "bpp_check_box: null pointer");
+    int grid = 0;
+    if (int rc = stateless_grid(n, &grid)) return rc;   // device capability check
+    BPP_CUDA(launch_check_box(plain, query, n, L, W, H, variant, out, as_stream(stream)));
+    g_launches.fetch_add(1);
+    return BPP_OK;
+}
+
+int32_t bpp_export_state(bpp_env *env, int32_t *plain, int32_t *box, int32_t *counter, int32_t *vol, void *stream)
+{
+    if (int rc = enter(env, "bpp_export_state")) return rc;
+    BPP_CUDA(launch_export_state(env->p, plain, box, counter, vol, as_stream(stream)));
+    g_launches.fetch_add(1);
+    return BPP_OK;
+}
+
+int32_t bpp_import_state(bpp_env *env, const int32_t *plain, const int32_t *box, const int32_t *counter,
+                         const int32_t *vol, void *stream)
+{
+    if (int rc = enter(env, "bpp_import_state")) return rc;
+    BPP_CUDA(launch_import_state(env->p, plain, box, counter, vol, as_stream(stream)));
+    g_launches.fetch_add(1);
+    env->was_reset = true;
+    return BPP_OK;
+}
+
+int32_t bpp_metrics_host(bpp_env *env, uint64_t *out_host, void *stream)
+{
+    if (int rc = enter(env, "bpp_metrics_host")) return rc;
+    if (!out_host) return fail(BPP_ERR_INVALID, "bpp_metrics_host: null pointer");
+    unsigned long long tmp[4] = {0, 0, 0, 0};
+    BPP_CUDA(cudaMemcpyAsync(tmp, env->d_metrics, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, as_stream(stream)));
+    BPP_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    out_host[0] = tmp[0]; out_host[1] = tmp[1]; out_host[2] = tmp[2]; out_host[3] = env->steps;
+    return BPP_OK;
+}
+
+int32_t bpp_debug_draws(uint64_t seed, uint32_t domain, uint32_t aux, uint64_t gid, int32_t n, uint32_t *out, void *stream)
+{
+    if (n < 0 || (n > 0 && !out)) return fail(BPP_ERR_INVALID, "bpp_debug_draws: bad arguments");
+    BPP_CUDA(launch_debug_draws(seed, domain, aux, gid, n, out, as_stream(stream)));
+    g_launches.fetch_add(1);
+    return BPP_OK;
+}
+
+int32_t bpp_debug_curand_draws(uint64_t seed, uint64_t subsequence, int32_t n, uint32_t *out, void *stream)
+{
+    if (n < 0 || (n > 0 && !out)) return fail(BPP_ERR_INVALID, "bpp_debug_curand_draws: bad arguments");
+    BPP_CUDA(launch_debug_curand(seed, subsequence, n, out, as_stream(stream)));
+    g_launches.fetch_add(1);
+    return BPP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+// bpp_common.cuh -- shared device-side definitions of libbpp_b200 (sm_100a).
+//
+// Vocabulary follows the reference: a *bin* holds a heightmap ("plain", envs/bpp0/space.py:22), the
+// *box* is the item waiting to be placed (box_creator.preview(1)[0], envs/bpp0/bin3D.py:68-70).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bpp {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kMaxSide = 32;          // L, W <= 32 (reciprocal-multiply position decode, smem tile)
+constexpr unsigned kFull = 0xffffffffu;
+
+// Per-bin scalar state: 32 bytes = one DRAM sector, read with two broadcast 128-bit loads.
+struct __align__(16) BinScalars {
+    uint32_t box;       // x | y << 8 | z << 16  (the waiting item)
+    int32_t cnt;        // len(space.boxes)
+    int32_t vol;        // sum of placed item volumes (Space.get_ratio numerator, space.py:146-151)
+    uint32_t episode;   // auto-resets so far
+    uint32_t ctr;       // reset+step calls so far: Philox draw index
+    int32_t pos;        // position inside the replayed / pre-cut episode
+    int32_t ep_len;     // cut1/cut2: items in the current episode buffer
+    uint32_t traj;      // replay: trajectory row of the current episode
+};
+static_assert(sizeof(BinScalars) == 32, "BinScalars must be one 32-byte sector");
+
+enum Mode : int { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
+
+struct EnvParams {
+    int N, L, W, H, A, A_pad, M, M_pad;      // M = A * (1 + rot): mask length
+    int gen_kind;
+    int n_items;
+    const uint32_t *item_set;                // packed x | y<<8 | z<<16
+    int n_traj, traj_cap;
+    const uint32_t *traj;                    // [n_traj][traj_cap] packed
+    const int32_t *traj_len;
+    uint32_t first_mod, gn_mod;              // first_traj mod n_traj, global_n mod n_traj
+    uint32_t seed_lo, seed_hi;
+    unsigned long long global_offset;
+    double lwh;                              // L*W*H
+    uint8_t *hm;                             // [N][A_pad] heightmaps, uint8
+    BinScalars *sc;                          // [N]
+    const uint32_t *ep_items;                // cut1/cut2: [N][ep_cap] packed items of the current episode
+    int ep_cap;
+    unsigned long long *metrics;             // {episodes, sum counter, sum vol}
+};
+
+struct StepIO {
+    const long long *actions;   // [N] or null (reset / observe)
+    float *obs;                 // [N][4A]
+    float *mask;                // [N][M]
+    float *reward;              // [N]
+    uint8_t *done;              // [N]
+    int32_t *counter;           // [N]
+    float *ratio;               // [N]
+    long long *sample;          // [N]
+    int episode_inc;            // reset: 1 if the env had been reset before (LoadBoxCreator.index += 1)
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  Stream layout (DESIGN.md "RNG streams"):
+//   key = (seed lo, seed hi); ctr = (n >> 2, domain << 28 | aux, gid lo, gid hi); draw = word n & 3.
+// Domain 0 / aux 0 is exactly the curand() sequence after curand_init(seed, gid, 0).
+// ---------------------------------------------------------------------------------------------------
+enum Domain : uint32_t { kDomItem = 0, kDomSample = 1, kDomGen = 2 };
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ uint32_t draw(uint32_t seed_lo, uint32_t seed_hi, uint32_t domain, uint32_t aux,
+                                         unsigned long long gid, uint32_t n)
+{
+    const uint4 o = philox4x32_10(make_uint4(n >> 2, (domain << 28) | (aux & 0x0FFFFFFFu), (uint32_t)gid,
+                                             (uint32_t)(gid >> 32)),
+                                  make_uint2(seed_lo, seed_hi));
+    const uint32_t w = n & 3u;
+    return w == 0 ? o.x : (w == 1 ? o.y : (w == 2 ? o.z : o.w));
+}
+
+// floor(q / d) == (q * c_rcp16[d]) >> 16 for q < 1024, 1 <= d <= 32  (c_rcp16[d] = ceil(2^16 / d))
+__constant__ uint32_t c_rcp16[kMaxSide + 1] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115, 2048};
+__device__ __forceinline__ uint32_t rcp16(uint32_t d) { return c_rcp16[d]; }
+
+// ---------------------------------------------------------------------------------------------------
+// Feasibility of one footprint.  `w` points at the window's first cell in a row-major tile of pitch W.
+// Returns the resting height max_h or -1.  Thresholds are the exact integer forms of
+// max_area/area > 0.95 | 0.85 | 0.50 (envs/bpp0/space.py:137-141, acktr/utils.py:28-32).
+// ---------------------------------------------------------------------------------------------------
+template <int VARIANT>
+__device__ __forceinline__ int accept(int m, int cnt, int a, int z, int H, int c00, int c10, int c01, int c11)
+{
+    if (m + z > H) return -1;                            // space.py:134-135, utils.py:20-21
+    const bool full = 20 * cnt > 19 * a;
+    const bool most = 20 * cnt > 17 * a;
+    const bool half = 2 * cnt > a;
+    if (VARIANT == 1) {                                  // space.py:118-125,137-142
+        const int rm = max(max(c00, c10), max(c01, c11));
+        const int sc = (c00 == rm) + (c10 == rm) + (c01 == rm) + (c11 == rm);
+        if (sc < 3) return -1;
+        const bool top = rm == m;
+        return (full || (top && sc == 3 && most) || (top && sc == 4 && half)) ? m : -1;
+    } else {                                             // utils.py:23-33
+        const int nc = (c00 == m) + (c10 == m) + (c01 == m) + (c11 == m);
+        return (full || (nc == 3 && most) || (nc == 4 && half)) ? m : -1;
+    }
+}
+
+// One thread evaluates one footprint (used by the mask sweep: one lane per candidate position).
+template <int VARIANT, typename T>
+__device__ __forceinline__ int check_window(const T *w, int W, int x, int y, int z, int H)
+{
+    const int c00 = (int)w[0], c10 = (int)w[(x - 1) * W], c01 = (int)w[y - 1], c11 = (int)w[(x - 1) * W + y - 1];
+    if (VARIANT == 1) {                                  // early corner reject, space.py:122-125
+        const int rm = max(max(c00, c10), max(c01, c11));
+        if ((c00 == rm) + (c10 == rm) + (c01 == rm) + (c11 == rm) < 3) return -1;
+    }
+    int m = -1, cnt = 0;
+    for (int r = 0; r < x; ++r) {
+        const T *row = w + r * W;
+        for (int c = 0; c < y; ++c) {
+            const int h = (int)row[c];
+            cnt = h > m ? 1 : cnt + (h == m);
+            m = max(m, h);
+        }
+    }
+    return accept<VARIANT>(m, cnt, x * y, z, H, c00, c10, c01, c11);
+}
+
+// Mask of one orientation: lanes sweep the (L-x+1)(W-y+1) candidate positions of the tile, set
+// smask[i*W+j] = 1 where feasible, and return the number of feasible positions (warp-uniform).
+// acktr/utils.py:54-57 / envs/bpp0/bin3D.py:85-88.  smask must be zero on entry.
+template <int VARIANT>
+__device__ __forceinline__ int sweep_orientation(const uint8_t *tile, uint8_t *smask, int L, int W, int H,
+                                                 int x, int y, int z, int lane)
+{
+    const int ni = L - x + 1, nj = W - y + 1;
+    if (ni <= 0 || nj <= 0) return 0;
+    const int npos = ni * nj;
+    const uint32_t rcp = rcp16((uint32_t)nj);
+    int total = 0;
+    for (int p0 = 0; p0 < npos; p0 += 32) {
+        const int q = p0 + lane;
+        bool ok = false;
+        if (q < npos) {
+            const int i = (int)(((uint32_t)q * rcp) >> 16);
+            const int j = q - i * nj;
+            ok = check_window<VARIANT, uint8_t>(tile + i * W + j, W, x, y, z, H) >= 0;
+            if (ok) smask[i * W + j] = 1;
+        }
+        total += __popc(__ballot_sync(kFull, ok));
+    }
+    return total;
+}
+
+}  // namespace bpp

@@ -1,0 +1,325 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures recorded
+from the Python reference.  Integer outputs bit-exact; reward bit-exact in float32; ratio within 1e-6."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+ROLLOUTS = ["10_norot", "10_rot", "20_norot", "8x12x9_rot"]
+
+
+@pytest.fixture(scope="module")
+def env_mod():
+    import torch
+    import b200bpp
+    assert torch.cuda.is_available()
+    return b200bpp
+
+
+def t2n(t):
+    return t.detach().cpu().numpy()
+
+
+def test_philox_matches_oracle_and_curand(env_mod):
+    import torch
+    from b200bpp import _cabi
+    l = _cabi.lib()
+    n = 64
+    out = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for seed, dom, aux, gid in [(1234, 0, 0, 0), (1234, 0, 0, 77), (0xDEADBEEFCAFE, 1, 0, 2 ** 33 + 5), (7, 2, 12345, 9)]:
+        _cabi.check(l.bpp_debug_draws(seed, dom, aux, gid, n, C.c_void_p(out.data_ptr()), None))
+        got = t2n(out).view(np.uint32)
+        want = np.array([orc.draw(seed, dom, aux, gid, i) for i in range(n)], dtype=np.uint32)
+        assert np.array_equal(got, want)
+        if dom == 0 and aux == 0:   # the item stream is cuRAND's Philox4_32_10 stream (curand_init(seed, gid, 0))
+            ref = torch.zeros(n, dtype=torch.int32, device="cuda")
+            _cabi.check(l.bpp_debug_curand_draws(seed, gid, n, C.c_void_p(ref.data_ptr()), None))
+            assert np.array_equal(t2n(ref).view(np.uint32), want)
+
+
+@pytest.mark.parametrize("tag", ROLLOUTS)
+@pytest.mark.parametrize("variant", [1, 2])
+def test_golden_rollout(env_mod, golden_dir, tag, variant):
+    """Replays the traces recorded from the Python reference through the CUDA env."""
+    g = np.load(os.path.join(golden_dir, "ref_rollouts_%s.npz" % tag))
+    size, rot = tuple(int(v) for v in g["size"]), bool(g["rot"])
+    T, N = g["action"].shape
+    A = size[0] * size[1]
+    env = env_mod.BinPackingVecEnv(N, size, enable_rotation=rot, trajectories=(g["traj"], g["traj_len"]),
+                                   first_traj=0, mask_variant=variant)
+    want_mask = g["mask_v1"] if variant == 1 else g["mask_v2"]
+
+    def check(t):
+        obs = t2n(env.obs)
+        assert np.array_equal(obs[:, :A], g["hm"][t].astype(np.float32)), t
+        for c in range(3):
+            assert np.array_equal(obs[:, (c + 1) * A:(c + 2) * A], np.repeat(g["box"][t][:, c:c + 1], A, 1).astype(np.float32))
+        assert np.array_equal(t2n(env.location_masks), want_mask[t].astype(np.float32)), t
+        plain, box, _, _ = env.export_state()
+        assert np.array_equal(t2n(plain), g["hm"][t].astype(np.int32))
+        assert np.array_equal(t2n(box), g["box"][t].astype(np.int32))
+
+    env.reset()
+    check(0)
+    for t in range(T):
+        if t % 2 == 0:     # alternate the device-resident and the host-buffer entry points
+            import torch
+            env.step_device(torch.as_tensor(g["action"][t], device="cuda"))
+            reward, done, counter, ratio = t2n(env.reward_t), t2n(env.done_t), t2n(env.counter_t), t2n(env.ratio_t)
+        else:
+            _, r, d, infos = env.step(g["action"][t].reshape(-1, 1))
+            reward, done = r.numpy().reshape(-1), d.astype(np.uint8)
+            counter = np.array([infos[i]["counter"] for i in range(N)])
+            ratio = np.array([infos[i]["ratio"] for i in range(N)], dtype=np.float32)
+        assert np.array_equal(done, g["done"][t]), t
+        assert np.array_equal(counter, g["counter"][t]), t
+        assert np.array_equal(reward, g["reward"][t].astype(np.float32)), t
+        assert np.max(np.abs(ratio.astype(np.float64) - g["ratio"][t])) <= 1e-6
+        check(t + 1)
+    m = env.metrics()
+    assert m["episodes"] == int(g["done"].sum())
+    assert m["sum_counter"] == int(g["counter"][g["done"] == 1].sum())
+    assert m["steps"] == T * N
+    env.close()
+
+
+def run_against_oracle(env_mod, N, size, rot, variant, gen_kw, T, seed, offset=0, global_n=None, edge_every=0):
+    """Steps the CUDA env and the oracle with the device-sampled actions; compares everything."""
+    import torch
+    okw = dict(gen_kw)
+    env = env_mod.BinPackingVecEnv(N, size, enable_rotation=rot, mask_variant=variant, seed=seed,
+                                   global_offset=offset, global_n=global_n, want_sample=True, **gen_kw)
+    if "trajectories" in okw:
+        tr = okw.pop("trajectories")
+        okw.update(gen="replay", traj=tr[0], traj_len=tr[1])
+    else:
+        okw = dict(gen=okw.get("data_type", "rs"))
+    o = orc.OracleEnv(N, size, rot=rot, mask_variant=variant, seed=seed, global_offset=offset, global_n=global_n,
+                      first_traj=gen_kw.get("first_traj", 1), n_threads=0, **okw)
+    env.reset()
+    o.reset()
+    A = size[0] * size[1]
+    rng = np.random.default_rng(seed)
+    for t in range(T + 1):
+        assert np.array_equal(t2n(env.obs), o.obs), t
+        assert np.array_equal(t2n(env.location_masks), o.mask), t
+        assert np.array_equal(t2n(env.sample_t), o.sample), t
+        if t == T:
+            break
+        actions = o.sample.copy()
+        if edge_every and t % edge_every == 0:      # sprinkle out-of-range / quirk actions
+            k = rng.integers(0, N, max(1, N // 16))
+            actions[k] = rng.choice([A, -1, A * (2 if rot else 1) + 3, 0], size=k.shape[0]) if rot else rng.choice([A, -1, 0], size=k.shape[0])
+        env.step_device(torch.as_tensor(actions, device="cuda"))
+        o.step(actions)
+        assert np.array_equal(t2n(env.done_t), o.done), t
+        assert np.array_equal(t2n(env.counter_t), o.counter), t
+        assert np.array_equal(t2n(env.reward_t), o.reward), t
+        assert np.max(np.abs(t2n(env.ratio_t).astype(np.float64) - o.ratio)) <= 1e-6
+    plain, box, counter, vol = env.export_state()
+    oplain, obox, ocounter, ovol = o.get_state()
+    assert np.array_equal(t2n(plain), oplain) and np.array_equal(t2n(box), obox)
+    assert np.array_equal(t2n(counter), ocounter) and np.array_equal(t2n(vol), ovol)
+    m, om = env.metrics(), o.metrics()
+    assert m == om
+    env.close()
+    return m
+
+
+@pytest.mark.parametrize("rot", [False, True])
+@pytest.mark.parametrize("variant", [1, 2])
+def test_config2_rs_4096_bins(env_mod, rot, variant):
+    # BASELINE.json configs[1]: 4096 parallel bins, 10x10x10, rs sequence, mask bit-exact
+    m = run_against_oracle(env_mod, 4096, (10, 10, 10), rot, variant, dict(data_type="rs"), T=64, seed=1234, edge_every=7)
+    assert m["episodes"] > 4096
+
+
+def test_config3_cut2_replay_subsample(env_mod, golden_dir):
+    # configs[2]: cut_2.pt replayed; bin g, episode e plays trajectory (1 + g + e*N) mod 2100
+    d = np.load(os.path.join(golden_dir, "datasets.npz"))
+    run_against_oracle(env_mod, 1024, (10, 10, 10), False, 2, dict(trajectories=(d["cut_2"], d["cut_2_len"]), first_traj=1),
+                       T=128, seed=5, offset=3000, global_n=65536)
+
+
+def test_config4_20cube_subsample(env_mod):
+    # configs[3]: 20x20x20 bin, rs; parity subsample 256 bins x 128 steps
+    run_against_oracle(env_mod, 256, (20, 20, 20), False, 2, dict(data_type="rs"), T=128, seed=99, offset=1000, global_n=262144)
+
+
+def test_config5_rotation_cut2_shard(env_mod, golden_dir):
+    # configs[4]: rotation enabled, cut_2 replay, one shard of a 524288-bin job (rank 3 of 8)
+    d = np.load(os.path.join(golden_dir, "datasets.npz"))
+    run_against_oracle(env_mod, 512, (10, 10, 10), True, 2, dict(trajectories=(d["cut_2"], d["cut_2_len"]), first_traj=1),
+                       T=96, seed=8, offset=3 * 65536, global_n=524288, edge_every=5)
+
+
+def test_odd_sizes_scalar_store_path(env_mod):
+    # L*W not a multiple of 4 -> scalar stores; non-square; big item set incl. items larger than the bin
+    items = [(x, y, z) for x in (1, 3, 8) for y in (2, 7) for z in (1, 4)]
+    run_against_oracle(env_mod, 300, (7, 9, 6), True, 1, dict(data_type="rs", box_set=items), T=48, seed=3, edge_every=4)
+    run_against_oracle(env_mod, 64, (5, 5, 5), False, 2, dict(data_type="rs", box_set=[(1, 1, 1), (2, 2, 2), (5, 5, 1)]), T=48, seed=4)
+
+
+def test_sharding_is_transparent(env_mod):
+    # two half-size envs with global offsets reproduce one full env (what multi-GPU sharding relies on)
+    import torch
+    N = 512
+    full = env_mod.BinPackingVecEnv(N, seed=42, want_sample=True)
+    halves = [env_mod.BinPackingVecEnv(N // 2, seed=42, want_sample=True, global_offset=k * N // 2, global_n=N) for k in range(2)]
+    full.reset()
+    [h.reset() for h in halves]
+    for t in range(24):
+        cat = lambda name: torch.cat([getattr(h, name) for h in halves])
+        assert torch.equal(full.obs, cat("obs")) and torch.equal(full.location_masks, cat("location_masks"))
+        assert torch.equal(full.sample_t, cat("sample_t"))
+        full.step_device(full.sample_t.clone())
+        [h.step_device(h.sample_t.clone()) for h in halves]
+        assert torch.equal(full.reward_t, cat("reward_t")) and torch.equal(full.done_t, cat("done_t"))
+    ms = [h.metrics() for h in halves]
+    assert full.metrics()["episodes"] == sum(m["episodes"] for m in ms)
+    assert full.metrics()["sum_vol"] == sum(m["sum_vol"] for m in ms)
+
+
+def blocky_plains(rng, n, L, W, H):
+    plains = np.zeros((n, L, W), np.int32)
+    for p in plains:
+        for _ in range(rng.integers(0, 14)):
+            x, y = rng.integers(1, L + 1), rng.integers(1, W + 1)
+            i, j = rng.integers(0, L - x + 1), rng.integers(0, W - y + 1)
+            p[i:i + x, j:j + y] = min(H, p[i:i + x, j:j + y].max() + rng.integers(0, 4))
+    return plains
+
+
+@pytest.mark.parametrize("size", [(10, 10, 10), (20, 20, 20), (8, 12, 9)])
+def test_stateless_masks_and_check_box_fuzz(env_mod, size):
+    import torch
+    from b200bpp import utils
+    L, W, H = size
+    rng = np.random.default_rng(L * 100 + W)
+    n = 600
+    plains = blocky_plains(rng, n, L, W, H)
+    boxes = np.stack([rng.integers(1, min(L, 10) + 2, n), rng.integers(1, min(W, 10) + 2, n), rng.integers(1, 6, n)], 1).astype(np.int32)
+    obs = np.concatenate([plains.reshape(n, -1)] + [np.repeat(boxes[:, c:c + 1], L * W, 1) for c in range(3)], 1).astype(np.float32)
+    for rot in (False, True):
+        for variant in (1, 2):
+            want = np.stack([orc.mask(plains[i], boxes[i], size, rot, variant) for i in range(n)]).astype(np.float32)
+            got = t2n(utils.mask_batch(torch.as_tensor(obs), size, rot, variant))
+            assert np.array_equal(got, want)
+            got2 = t2n(utils.mask_from_plain(plains.reshape(n, -1), boxes, size, rot, variant))
+            assert np.array_equal(got2, want)
+    q = np.stack([boxes[:, 0], boxes[:, 1], rng.integers(-1, L, n), rng.integers(-1, W, n), boxes[:, 2]], 1).astype(np.int32)
+    for variant in (1, 2):
+        want = np.array([orc.check_box(plains[i], *q[i][:5], size, variant) for i in range(n)], np.int32)
+        assert np.array_equal(utils.check_box_batch(plains, q, size, variant), want)
+    # reference-signature single-observation helpers (acktr/utils.py:37-94)
+    assert utils.get_possible_position(torch.as_tensor(obs[0]).cuda(), size) == orc.mask(plains[0], boxes[0], size, False, 2).tolist()
+    assert utils.get_possible_position(obs[1], size) == orc.mask(plains[1], boxes[1], size, False, 2).tolist()
+    rm = utils.get_rotation_mask(torch.as_tensor(obs[2]), size)
+    assert rm.dtype == np.int32 and np.array_equal(rm, orc.mask(plains[2], boxes[2], size, True, 2))
+
+
+def test_v1_v2_divergence_on_device(env_mod):
+    from b200bpp import utils
+    plain = np.zeros((20, 20), np.int32)
+    plain[:7, :7] = 3
+    plain[0, 0] = plain[6, 6] = 0
+    assert utils.check_box(plain, 7, 7, 0, 0, 2, (20, 20, 20), 1) == -1
+    assert utils.check_box(plain, 7, 7, 0, 0, 2, (20, 20, 20), 2) == 3
+    m1 = t2n(utils.mask_from_plain(plain.reshape(1, -1), [[7, 7, 2]], (20, 20, 20), False, 1))[0]
+    m2 = t2n(utils.mask_from_plain(plain.reshape(1, -1), [[7, 7, 2]], (20, 20, 20), False, 2))[0]
+    assert m1[0] == 0 and m2[0] == 1
+
+
+def test_traj0_and_sentinel_on_device(env_mod, golden_dir):
+    from b200bpp import utils
+    g = np.load(os.path.join(golden_dir, "traj0.npz"))
+    plain = np.zeros((10, 10), np.int32)
+    for x, y, z, lx, ly, lz in g["placed"]:
+        for variant in (1, 2):
+            assert utils.check_box(plain, x, y, lx, ly, z, (10, 10, 10), variant) == lz
+        plain[lx:lx + x, ly:ly + y] = lz + z
+    m = t2n(utils.mask_from_plain(plain.reshape(1, -1), [g["last"]], (10, 10, 10), False, 2))
+    assert m.all()      # no feasible position -> all-ones fallback
+
+
+def test_vecenv_surface(env_mod):
+    """What acktr/envs.py:77-118 hands to main.py: shapes, dtypes, devices, infos."""
+    import torch
+    env = env_mod.make_vec_envs("Bpp-v0", 1, 16, 0.99, None, "cuda:0", False,
+                                args=type("A", (), dict(container_size=(10, 10, 10), enable_rotation=True,
+                                                        box_size_set=env_mod.default_item_set(), data_type="rs")))
+    assert env.num_envs == 16 and env.observation_space.shape == (400,) and env.action_space.n == 200
+    assert env.action_space.__class__.__name__ == "Discrete"
+    obs = env.reset()
+    assert obs.shape == (16, 400) and obs.dtype == torch.float32 and obs.is_cuda
+    assert env.location_masks.shape == (16, 200)
+    a = torch.zeros((16, 1), dtype=torch.int64, device="cuda")
+    a[0, 0] = 100      # action == A: un-rotated and out of bounds (bin3D.py:102) -> episode ends
+    obs, reward, done, infos = env.step(a)
+    assert reward.shape == (16, 1) and reward.dtype == torch.float32 and not reward.is_cuda
+    assert done.dtype == np.bool_ and done.shape == (16,) and done[0]
+    assert len(infos) == 16 and "episode" in infos[0] and infos[0]["episode"]["l"] == 1
+    assert not done[1] and infos[1]["counter"] == 1 and abs(infos[1]["ratio"] - reward[1, 0].item() / 10) < 1e-6
+    from b200bpp.utils import get_vec_normalize
+    assert get_vec_normalize(env) is None
+    env.close()
+
+
+def test_errors_are_loud(env_mod):
+    import torch
+    from b200bpp import BppError
+    env = env_mod.BinPackingVecEnv(8)
+    with pytest.raises(BppError):
+        env.step_device(torch.zeros(8, dtype=torch.int64, device="cuda"))     # step before reset
+    env.reset()
+    with pytest.raises(ValueError):
+        env.step_device(torch.zeros(9, dtype=torch.int64, device="cuda"))
+    with pytest.raises(BppError):
+        env_mod.BinPackingVecEnv(8, container_size=(40, 10, 10))
+    with pytest.raises(BppError):
+        env_mod.BinPackingVecEnv(8, data_type="cut1")     # not in this build yet -> loud, no fallback
+
+
+def test_full_size_properties(env_mod):
+    """BASELINE sizes through size-independent properties; a prefix of the bins is also checked against the oracle."""
+    import torch
+    for N, size, T in ((65536, (10, 10, 10), 48), (262144, (20, 20, 20), 24)):
+        L, W, H = size
+        A = L * W
+        env = env_mod.BinPackingVecEnv(N, size, seed=77, want_sample=True)
+        K = 128
+        o = orc.OracleEnv(K, size, seed=77, global_n=N, n_threads=0)
+        env.reset()
+        o.reset()
+        ep = 0
+        vol_done = 0
+        for t in range(T):
+            assert torch.equal(env.obs[:K].cpu(), torch.from_numpy(o.obs))
+            assert torch.equal(env.location_masks[:K].cpu(), torch.from_numpy(o.mask))
+            mask = env.location_masks
+            assert bool(((mask == 0) | (mask == 1)).all()) and bool((mask.sum(1) >= 1).all())
+            assert bool((env.obs[:, :A] <= H).all()) and bool((env.obs[:, :A] >= 0).all())
+            for c in range(1, 4):    # box planes are constant
+                plane = env.obs[:, c * A:(c + 1) * A]
+                assert bool((plane == plane[:, :1]).all())
+            # the sampled action is valid under the mask
+            assert bool((mask.gather(1, env.sample_t.view(-1, 1)) == 1).all())
+            actions = env.sample_t.clone()
+            env.step_device(actions)
+            o.step(t2n(actions[:K]))
+            assert np.array_equal(t2n(env.done_t[:K]), o.done) and np.array_equal(t2n(env.reward_t[:K]), o.reward)
+            ep += int(env.done_t.sum())
+            vol_done += int((env.ratio_t.double() * (L * W * H)).round().long()[env.done_t.bool()].sum())
+            # reward is 10 * item volume / LWH exactly when not done, 0 when done
+            assert bool((env.reward_t[env.done_t.bool()] == 0).all())
+        plain, box, counter, vol = env.export_state()
+        assert bool((plain.sum(1) >= vol).all())            # placed volume never exceeds the volume under the heightmap
+        assert bool((plain.max(1).values <= H).all())
+        m = env.metrics()
+        assert m["episodes"] == ep and m["steps"] == N * T and m["sum_vol"] == vol_done
+        env.close()
