@@ -96,9 +96,12 @@ def run_against_oracle(env_mod, N, size, rot, variant, gen_kw, T, seed, offset=0
                                    global_offset=offset, global_n=global_n, want_sample=True, **gen_kw)
     if "trajectories" in okw:
         tr = okw.pop("trajectories")
+        okw.pop("first_traj", None)
         okw.update(gen="replay", traj=tr[0], traj_len=tr[1])
     else:
         okw = dict(gen=okw.get("data_type", "rs"))
+        if "box_set" in gen_kw:
+            okw["item_set"] = np.asarray(gen_kw["box_set"], np.uint8)
     o = orc.OracleEnv(N, size, rot=rot, mask_variant=variant, seed=seed, global_offset=offset, global_n=global_n,
                       first_traj=gen_kw.get("first_traj", 1), n_threads=0, **okw)
     env.reset()
