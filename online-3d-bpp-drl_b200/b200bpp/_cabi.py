@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbpp_b200.so")
+# BPP_B200_LIB lets kernel experiments A/B a differently built library; the default is the in-tree build
+LIB_PATH = os.environ.get("BPP_B200_LIB") or os.path.join(_HERE, "libbpp_b200.so")
 
 ABI_VERSION = 1
 GEN_RS, GEN_REPLAY, GEN_CUT1, GEN_CUT2 = 0, 1, 2, 3

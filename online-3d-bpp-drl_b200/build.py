@@ -30,16 +30,22 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out/defines build an experimental variant (e.g. defines=["BPP_MIN_BLOCKS=6"]) next to the default."""
+    if out is None and not force and up_to_date():
         return OUT
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    out = out or OUT
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
     env = dict(os.environ)
     env.pop("CC", None)      # the image exports a gcc wrapper in $CC that nvcc must not pick up
     env.pop("CXX", None)
     subprocess.check_call(cmd, cwd=CSRC, env=env)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=os.path.abspath(outs[0]) if outs else None,
+                defines=defs))

@@ -118,7 +118,7 @@ int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
     p.gen_kind = cfg->gen_kind;
     p.seed_lo = (uint32_t)cfg->seed; p.seed_hi = (uint32_t)(cfg->seed >> 32);
     p.global_offset = (unsigned long long)cfg->global_offset;
-    p.lwh = (double)cfg->L * (double)cfg->W * (double)cfg->H;
+    p.lwh_f = (float)(cfg->L * cfg->W * cfg->H);
     const long long global_n = cfg->global_n > 0 ? cfg->global_n : cfg->n_bins;
 
 #define BPP_CREATE_CUDA(expr)                                                                       \

@@ -40,7 +40,7 @@ struct EnvParams {
     uint32_t first_mod, gn_mod;              // first_traj mod n_traj, global_n mod n_traj
     uint32_t seed_lo, seed_hi;
     unsigned long long global_offset;
-    double lwh;                              // L*W*H
+    float lwh_f;                             // L*W*H (< 2^24, exact in float32)
     uint8_t *hm;                             // [N][A_pad] heightmaps, uint8
     BinScalars *sc;                          // [N]
     const uint32_t *ep_items;                // cut1/cut2: [N][ep_cap] packed items of the current episode
@@ -96,16 +96,28 @@ __device__ __forceinline__ uint32_t rcp16(uint32_t d) { return c_rcp16[d]; }
 
 // ---------------------------------------------------------------------------------------------------
 // Feasibility of one footprint.  `w` points at the window's first cell in a row-major tile of pitch W.
-// Returns the resting height max_h or -1.  Thresholds are the exact integer forms of
-// max_area/area > 0.95 | 0.85 | 0.50 (envs/bpp0/space.py:137-141, acktr/utils.py:28-32).
+// Returns the resting height max_h or -1.  The reference's float tests max_area/area > 0.95 | 0.85 | 0.50
+// (envs/bpp0/space.py:137-141, acktr/utils.py:28-32) are the exact integer tests 20*ma > 19*a,
+// 20*ma > 17*a, 2*ma > a, i.e. ma >= floor(19a/20)+1, floor(17a/20)+1, floor(a/2)+1: three thresholds
+// that depend only on the footprint area and are computed once per orientation.
 // ---------------------------------------------------------------------------------------------------
+struct Thresholds {
+    int full, most, half;
+};
+__device__ __forceinline__ Thresholds make_thresholds(int a)
+{
+    Thresholds t;
+    t.full = (19 * a) / 20 + 1;
+    t.most = (17 * a) / 20 + 1;
+    t.half = a / 2 + 1;
+    return t;
+}
+
 template <int VARIANT>
-__device__ __forceinline__ int accept(int m, int cnt, int a, int z, int H, int c00, int c10, int c01, int c11)
+__device__ __forceinline__ int accept(int m, int cnt, Thresholds t, int z, int H, int c00, int c10, int c01, int c11)
 {
     if (m + z > H) return -1;                            // space.py:134-135, utils.py:20-21
-    const bool full = 20 * cnt > 19 * a;
-    const bool most = 20 * cnt > 17 * a;
-    const bool half = 2 * cnt > a;
+    const bool full = cnt >= t.full, most = cnt >= t.most, half = cnt >= t.half;
     if (VARIANT == 1) {                                  // space.py:118-125,137-142
         const int rm = max(max(c00, c10), max(c01, c11));
         const int sc = (c00 == rm) + (c10 == rm) + (c01 == rm) + (c11 == rm);
@@ -118,25 +130,66 @@ __device__ __forceinline__ int accept(int m, int cnt, int a, int z, int H, int c
     }
 }
 
-// One thread evaluates one footprint (used by the mask sweep: one lane per candidate position).
-template <int VARIANT, typename T>
-__device__ __forceinline__ int check_window(const T *w, int W, int x, int y, int z, int H)
+// (max, number of cells equal to the max) of an x-by-y window; one pass, any size.
+template <typename T>
+__device__ __forceinline__ void window_stats(const T *w, int W, int x, int y, int &m, int &cnt)
 {
-    const int c00 = (int)w[0], c10 = (int)w[(x - 1) * W], c01 = (int)w[y - 1], c11 = (int)w[(x - 1) * W + y - 1];
-    if (VARIANT == 1) {                                  // early corner reject, space.py:122-125
-        const int rm = max(max(c00, c10), max(c01, c11));
-        if ((c00 == rm) + (c10 == rm) + (c01 == rm) + (c11 == rm) < 3) return -1;
-    }
-    int m = -1, cnt = 0;
+    m = -1;
+    cnt = 0;
+#pragma unroll 1
     for (int r = 0; r < x; ++r) {
         const T *row = w + r * W;
+#pragma unroll 1
         for (int c = 0; c < y; ++c) {
             const int h = (int)row[c];
             cnt = h > m ? 1 : cnt + (h == m);
             m = max(m, h);
         }
     }
-    return accept<VARIANT>(m, cnt, x * y, z, H, c00, c10, c01, c11);
+}
+
+// Same for a compile-time footprint: all cells go to registers, max tree, then equality count.
+template <int X, int Y>
+__device__ __forceinline__ void window_stats_fixed(const uint8_t *w, int W, int &m, int &cnt)
+{
+    int h[X * Y];
+#pragma unroll
+    for (int r = 0; r < X; ++r)
+#pragma unroll
+        for (int c = 0; c < Y; ++c) h[r * Y + c] = w[r * W + c];
+    m = h[0];
+#pragma unroll
+    for (int k = 1; k < X * Y; ++k) m = max(m, h[k]);
+    int below = 0;                       // cells strictly below the max: min(m - h, 1) is 0 or 1
+#pragma unroll
+    for (int k = 0; k < X * Y; ++k) below += min(m - h[k], 1);
+    cnt = X * Y - below;
+}
+
+// One thread evaluates one footprint on int32 heightmaps (batched check_box entry point).
+template <int VARIANT, typename T>
+__device__ __forceinline__ int check_window(const T *w, int W, int x, int y, int z, int H)
+{
+    const int c00 = (int)w[0], c10 = (int)w[(x - 1) * W], c01 = (int)w[y - 1], c11 = (int)w[(x - 1) * W + y - 1];
+    int m, cnt;
+    window_stats<T>(w, W, x, y, m, cnt);
+    return accept<VARIANT>(m, cnt, make_thresholds(x * y), z, H, c00, c10, c01, c11);
+}
+
+// (max, count) of the footprint with the window code unrolled for the reference's item range (1..5 per side,
+// --item-size-range, acktr/arguments.py:30): `code` = (x-1)*5 + (y-1), or -1 for any other size.  The switch is
+// warp-uniform (one indirect branch per candidate position); only the window code is specialised so that
+// the instruction footprint stays inside the instruction cache.
+__device__ __forceinline__ void window_stats_switch(const uint8_t *w, int W, int x, int y, int code, int &m, int &cnt)
+{
+#define BPP_WS_CASE(X, Y) case ((X) - 1) * 5 + ((Y) - 1): window_stats_fixed<X, Y>(w, W, m, cnt); break;
+#define BPP_WS_ROW(X) BPP_WS_CASE(X, 1) BPP_WS_CASE(X, 2) BPP_WS_CASE(X, 3) BPP_WS_CASE(X, 4) BPP_WS_CASE(X, 5)
+    switch (code) {
+        BPP_WS_ROW(1) BPP_WS_ROW(2) BPP_WS_ROW(3) BPP_WS_ROW(4) BPP_WS_ROW(5)
+    default: window_stats<uint8_t>(w, W, x, y, m, cnt); break;
+    }
+#undef BPP_WS_ROW
+#undef BPP_WS_CASE
 }
 
 // Mask of one orientation: lanes sweep the (L-x+1)(W-y+1) candidate positions of the tile, set
@@ -146,18 +199,26 @@ template <int VARIANT>
 __device__ __forceinline__ int sweep_orientation(const uint8_t *tile, uint8_t *smask, int L, int W, int H,
                                                  int x, int y, int z, int lane)
 {
+    if (x > L || y > W) return 0;                        // range(width - x + 1) empty, utils.py:54-55
     const int ni = L - x + 1, nj = W - y + 1;
-    if (ni <= 0 || nj <= 0) return 0;
     const int npos = ni * nj;
     const uint32_t rcp = rcp16((uint32_t)nj);
+    const Thresholds th = make_thresholds(x * y);
+    const int o10 = (x - 1) * W, o01 = y - 1;
+    const int code = (x <= 5 && y <= 5) ? (x - 1) * 5 + (y - 1) : -1;
     int total = 0;
+#pragma unroll 1
     for (int p0 = 0; p0 < npos; p0 += 32) {
         const int q = p0 + lane;
         bool ok = false;
         if (q < npos) {
             const int i = (int)(((uint32_t)q * rcp) >> 16);
             const int j = q - i * nj;
-            ok = check_window<VARIANT, uint8_t>(tile + i * W + j, W, x, y, z, H) >= 0;
+            const uint8_t *w = tile + i * W + j;
+            const int c00 = w[0], c10 = w[o10], c01 = w[o01], c11 = w[o10 + o01];
+            int m, cnt;
+            window_stats_switch(w, W, x, y, code, m, cnt);
+            ok = accept<VARIANT>(m, cnt, th, z, H, c00, c10, c01, c11) >= 0;
             if (ok) smask[i * W + j] = 1;
         }
         total += __popc(__ballot_sync(kFull, ok));

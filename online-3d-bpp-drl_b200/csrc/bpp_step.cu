@@ -15,6 +15,10 @@
 #include "bpp_common.cuh"
 #include "bpp_launch.h"
 
+#ifndef BPP_MIN_BLOCKS
+#define BPP_MIN_BLOCKS 4   // resident CTAs per SM the register allocator must allow (8 warps each)
+#endif
+
 namespace bpp {
 
 __device__ __forceinline__ float4 bytes_to_float4(uint32_t w)
@@ -23,29 +27,30 @@ __device__ __forceinline__ float4 bytes_to_float4(uint32_t w)
                        (float)(w >> 24));
 }
 
-// Next item of the bin's sequence (box_creator.preview(1)[0]).
-__device__ __forceinline__ uint32_t fetch_item(const EnvParams &p, const BinScalars &s, unsigned long long gid,
-                                               long long bin)
+constexpr uint32_t kSentinel10 = 10u | (10u << 8) | (10u << 16);   // binCreator.py:62,69-71; mdCreator.py:161
+
+// Item at position `pos` of replay trajectory `t` (LoadBoxCreator, envs/bpp0/binCreator.py:64-72).
+__device__ __forceinline__ uint32_t replay_item(const EnvParams &p, uint32_t t, int pos)
 {
-    switch (p.gen_kind) {
-    case 0: {   // rs: RandomBoxCreator.generate_box_size, envs/bpp0/binCreator.py:38-40
-        const uint32_t u = draw(p.seed_lo, p.seed_hi, kDomItem, 0, gid, s.ctr);
-        return __ldg(p.item_set + __umulhi(u, (uint32_t)p.n_items));
-    }
-    case 1: {   // replay: LoadBoxCreator, binCreator.py:51-72 (sentinel (10,10,10) past the row, hard-coded)
-        if (s.pos < __ldg(p.traj_len + s.traj)) return __ldg(p.traj + (size_t)s.traj * p.traj_cap + s.pos);
-        return 10u | (10u << 8) | (10u << 16);
-    }
-    default: {  // cut1 / cut2: pre-cut episode buffer; sentinels cutCreator.py:113-115 / mdCreator.py:161
-        if (s.pos < s.ep_len) return __ldg(p.ep_items + (size_t)bin * p.ep_cap + s.pos);
-        return p.gen_kind == 2 ? ((uint32_t)p.L | ((uint32_t)p.W << 8) | ((uint32_t)p.H << 16))
-                               : (10u | (10u << 8) | (10u << 16));
-    }
-    }
+    return pos < __ldg(p.traj_len + t) ? __ldg(p.traj + (size_t)t * p.traj_cap + pos) : kSentinel10;
 }
 
+// Item at position `pos` of the bin's pre-cut episode (cut1: cutCreator.py:112-128, cut2: mdCreator.py:163-166).
+__device__ __forceinline__ uint32_t episode_item(const EnvParams &p, long long bin, int pos, int ep_len)
+{
+    if (pos < ep_len) return __ldg(p.ep_items + (size_t)bin * p.ep_cap + pos);
+    return p.gen_kind == 2 ? ((uint32_t)p.L | ((uint32_t)p.W << 8) | ((uint32_t)p.H << 16)) : kSentinel10;
+}
+
+// The kernel works on batches of 32 bins per warp in three phases:
+//   A  (lane = bin)   scalar work once per bin instead of once per lane: state record, action decode,
+//                     Philox draws, both candidates for the next item (placement succeeds / episode ends);
+//   B  (warp = bin)   for each of the 32 bins in turn: heightmap tile, placement check + update, mask
+//                     sweep, tile / observation / mask write-back, action sampling; the per-bin scalars
+//                     arrive by warp shuffle from the lane that owns the bin;
+//   A2 (lane = bin)   reward, done, info, new state record, coalesced stores, episode metrics.
 template <int ROT, int VARIANT, bool VEC4>
-__global__ void __launch_bounds__(kThreads) bpp_step_kernel(const EnvParams p, const StepIO io, const int mode)
+__global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(const EnvParams p, const StepIO io, const int mode)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ unsigned long long blk_metrics[3];
@@ -54,190 +59,281 @@ __global__ void __launch_bounds__(kThreads) bpp_step_kernel(const EnvParams p, c
     const int warp = threadIdx.x >> 5;
     uint8_t *tile = smem + (size_t)warp * (p.A_pad + p.M_pad);
     uint8_t *smask = tile + p.A_pad;
+    uint4 *tile4 = reinterpret_cast<uint4 *>(tile);
+    uint4 *smask4 = reinterpret_cast<uint4 *>(smask);
     const int L = p.L, W = p.W, H = p.H, A = p.A;
+    const int nq_tile = p.A_pad >> 4, nq_mask = p.M_pad >> 4;     // 128-bit words per tile
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    const uint32_t rcpW = rcp16((uint32_t)W);
+    const bool fresh_reset = mode == kModeReset && !io.episode_inc;
 
     if (threadIdx.x < 3) blk_metrics[threadIdx.x] = 0ull;
     __syncthreads();
     unsigned long long m_ep = 0, m_cnt = 0, m_vol = 0;
 
-    for (long long bin = (long long)blockIdx.x * kWarpsPerBlock + warp; bin < p.N;
-         bin += (long long)gridDim.x * kWarpsPerBlock) {
-        const unsigned long long gid = p.global_offset + (unsigned long long)bin;
+    const long long n_batches = ((long long)p.N + 31) >> 5;
+    for (long long batch = (long long)blockIdx.x * kWarpsPerBlock + warp; batch < n_batches;
+         batch += (long long)gridDim.x * kWarpsPerBlock) {
+        const long long bin0 = batch << 5;
+        const long long mybin = bin0 + lane;
+        const bool have = mybin < p.N;
+        const int nb = (int)min(32ll, (long long)p.N - bin0);
+        const unsigned long long gid = p.global_offset + (unsigned long long)mybin;
 
-        // ---- 1. load state ------------------------------------------------------------------------
-        BinScalars s;
-        {
-            const uint4 *sp = reinterpret_cast<const uint4 *>(p.sc + bin);
+        // ---- phase A: lane = bin ----------------------------------------------------------------------
+        BinScalars s = {};
+        long long action = -1;
+        if (have) {
+            const uint4 *sp = reinterpret_cast<const uint4 *>(p.sc + mybin);
             const uint4 a = sp[0], b = sp[1];
             s.box = a.x; s.cnt = (int)a.y; s.vol = (int)a.z; s.episode = a.w;
             s.ctr = b.x; s.pos = (int)b.y; s.ep_len = (int)b.z; s.traj = b.w;
+            if (mode == kModeStep) action = io.actions[mybin];
         }
-        uint4 *tile4 = reinterpret_cast<uint4 *>(tile);
-        if (mode == kModeReset) {
-            for (int k = lane; k < p.A_pad / 16; k += 32) tile4[k] = make_uint4(0, 0, 0, 0);
-        } else {
-            const uint4 *g = reinterpret_cast<const uint4 *>(p.hm + (size_t)bin * p.A_pad);
-            for (int k = lane; k < p.A_pad / 16; k += 32) tile4[k] = g[k];
-        }
-        for (int k = lane; k < p.M_pad / 16; k += 32)
-            reinterpret_cast<uint4 *>(smask)[k] = make_uint4(0, 0, 0, 0);
-        __syncwarp();
-
-        // ---- 2. step --------------------------------------------------------------------------------
-        float reward = 0.f;
-        int done = 0;
-        bool new_episode = false;
+        if (fresh_reset) { s.episode = 0; s.ctr = 0; }
+        // action decode, envs/bpp0/bin3D.py:100-105 (strict '>': action == A stays un-rotated and falls out
+        // of bounds; without rotation an action > A trips the reference's assert, here it is infeasible)
+        // and Space.idx_to_position, space.py:153-156.  act = lx | ly << 8 | flag << 16 | valid << 17
+        uint32_t act = 0;
         if (mode == kModeStep) {
-            const int bx = s.box & 0xff, by = (s.box >> 8) & 0xff, bz = (s.box >> 16) & 0xff;
-            long long idx = io.actions[bin];
-            bool flag = false;
-            // envs/bpp0/bin3D.py:100-105: strict '>' -- action == A stays un-rotated and falls out of
-            // bounds; without rotation an action > A trips the reference's assert, here it is infeasible.
-            if (idx > A) { if (ROT) { idx -= A; flag = true; } else idx = -1; }
-            const int x = flag ? by : bx, y = flag ? bx : by, z = bz;      // space.py:166-172
-            int new_h = -1;
+            long long idx = action;
+            uint32_t flag = 0;
+            if (idx > A) { if (ROT) { idx -= A; flag = 1; } else idx = -1; }
             if (idx >= 0 && idx < A) {
-                const int lx = (int)idx / W, ly = (int)idx - lx * W;         // space.py:153-156
-                if (lx + x <= L && ly + y <= W) {                            // space.py:112-113
-                    // Space.check_box (space.py:116-144), lanes over the footprint
-                    const uint8_t *w = tile + lx * W + ly;
-                    const int a = x * y;
-                    const uint32_t rcp = rcp16((uint32_t)y);
-                    int m = -1;
-                    for (int q = lane; q < a; q += 32) {
-                        const int r = (int)(((uint32_t)q * rcp) >> 16), c = q - r * y;
-                        m = max(m, (int)w[r * W + c]);
-                    }
-                    m = __reduce_max_sync(kFull, m);
-                    int cnt = 0;
-                    for (int q = lane; q < a; q += 32) {
-                        const int r = (int)(((uint32_t)q * rcp) >> 16), c = q - r * y;
-                        cnt += (w[r * W + c] == m);
-                    }
-                    cnt = __reduce_add_sync(kFull, cnt);
-                    new_h = accept<1>(m, cnt, a, z, H, w[0], w[(x - 1) * W], w[y - 1], w[(x - 1) * W + y - 1]);
-                    if (new_h >= 0) {                                        // update_height_graph, space.py:36-46
-                        __syncwarp();
-                        const uint8_t top = (uint8_t)(new_h + z);
-                        for (int q = lane; q < a; q += 32) {
-                            const int r = (int)(((uint32_t)q * rcp) >> 16), c = q - r * y;
-                            tile[lx * W + ly + r * W + c] = top;
-                        }
-                    }
-                }
-            }
-            if (new_h < 0) {                                                 // bin3D.py:108-112
-                done = 1;
-                if (lane == 0) {
-                    if (io.reward) io.reward[bin] = 0.f;
-                    if (io.done) io.done[bin] = 1;
-                    if (io.counter) io.counter[bin] = s.cnt;
-                    if (io.ratio) io.ratio[bin] = (float)((double)s.vol / p.lwh);
-                }
-                m_ep += 1; m_cnt += (unsigned long long)s.cnt; m_vol += (unsigned long long)s.vol;
-                new_episode = true;
-                s.episode += 1;
-                __syncwarp();
-                for (int k = lane; k < p.A_pad / 16; k += 32) tile4[k] = make_uint4(0, 0, 0, 0);
-            } else {                                                         // bin3D.py:114-127
-                const int v = bx * by * bz;
-                s.cnt += 1; s.vol += v; s.pos += 1;
-                reward = (float)(((double)v / p.lwh) * 10.0);               // bin3D.py:44-46,121
-                if (lane == 0) {
-                    if (io.reward) io.reward[bin] = reward;
-                    if (io.done) io.done[bin] = 0;
-                    if (io.counter) io.counter[bin] = s.cnt;
-                    if (io.ratio) io.ratio[bin] = (float)((double)s.vol / p.lwh);   // space.py:146-151
-                }
-            }
-        } else if (mode == kModeReset) {
-            new_episode = true;
-            s.episode += (uint32_t)io.episode_inc;
-            if (!io.episode_inc) { s.episode = 0; s.ctr = 0; }
-        }
-        if (new_episode) {                                                   // PackingGame.reset, bin3D.py:55-59
-            s.cnt = 0; s.vol = 0; s.pos = 0;
-            if (p.gen_kind == 1) {                                           // trajectory of (gid, episode)
-                if (mode == kModeReset && !io.episode_inc)
-                    s.traj = (uint32_t)((p.first_mod + gid % (unsigned long long)p.n_traj) % (unsigned long long)p.n_traj);
-                else { s.traj += p.gn_mod; if (s.traj >= (uint32_t)p.n_traj) s.traj -= (uint32_t)p.n_traj; }
+                const uint32_t lx = ((uint32_t)idx * rcpW) >> 16, ly = (uint32_t)idx - lx * (uint32_t)W;
+                act = lx | (ly << 8) | (flag << 16) | (1u << 17);
             }
         }
-        if (mode != kModeObserve) s.box = fetch_item(p, s, gid, bin);
-        __syncwarp();
+        // Philox draws of this step (counter n = s.ctr): item stream (rs) and action-sampler stream
+        uint32_t u_samp = 0;
+        uint32_t next_ok = s.box, next_new = s.box;      // waiting item if the placement succeeds / a new episode starts
+        uint32_t traj_new = s.traj;
+        if (have && mode != kModeObserve) {
+            switch (p.gen_kind) {
+            case 0: {   // rs: RandomBoxCreator.generate_box_size, envs/bpp0/binCreator.py:38-40 -- same draw either way
+                const uint32_t u = draw(p.seed_lo, p.seed_hi, kDomItem, 0, gid, s.ctr);
+                next_ok = next_new = __ldg(p.item_set + __umulhi(u, (uint32_t)p.n_items));
+                break;
+            }
+            case 1: {   // replay: LoadBoxCreator.reset / generate_box_size, binCreator.py:51-72
+                if (fresh_reset) traj_new = (uint32_t)((p.first_mod + gid % (unsigned long long)p.n_traj) % (unsigned long long)p.n_traj);
+                else { traj_new = s.traj + p.gn_mod; if (traj_new >= (uint32_t)p.n_traj) traj_new -= (uint32_t)p.n_traj; }
+                next_new = replay_item(p, traj_new, 0);
+                if (mode == kModeStep) next_ok = replay_item(p, s.traj, s.pos + 1);
+                break;
+            }
+            default: {  // cut1 / cut2 episode buffers
+                next_new = episode_item(p, mybin, 0, s.ep_len);
+                if (mode == kModeStep) next_ok = episode_item(p, mybin, s.pos + 1, s.ep_len);
+                break;
+            }
+            }
+        }
+        if (have && io.sample) u_samp = draw(p.seed_lo, p.seed_hi, kDomSample, 0, gid, s.ctr);
+        uint32_t my_res = 0;      // from phase B: bit 31 = placement succeeded, low bits = sampled action
 
-        // ---- 3. ground-truth mask of the new state -------------------------------------------------
-        const int bx = s.box & 0xff, by = (s.box >> 8) & 0xff, bz = (s.box >> 16) & 0xff;
-        int total = 0;
-        if (io.mask || io.sample) {
-            total = sweep_orientation<VARIANT>(tile, smask, L, W, H, bx, by, bz, lane);
-            if (ROT) total += sweep_orientation<VARIANT>(tile, smask + A, L, W, H, by, bx, bz, lane);
+        // ---- phase B: warp = bin ----------------------------------------------------------------------
+        uint4 pre = zero4;        // next bin's tile words, prefetched while the current bin is processed
+        const bool use_pre = nq_tile <= 32 && mode != kModeReset;
+        if (use_pre && lane < nq_tile) pre = reinterpret_cast<const uint4 *>(p.hm + (size_t)bin0 * p.A_pad)[lane];
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            const long long bin = bin0 + b;
+            const uint32_t box = __shfl_sync(kFull, s.box, b);
+            const uint32_t bact = __shfl_sync(kFull, act, b);
+            const uint32_t b_ok = __shfl_sync(kFull, next_ok, b);
+            const uint32_t b_new = __shfl_sync(kFull, next_new, b);
+            const uint32_t b_us = __shfl_sync(kFull, u_samp, b);
+            uint8_t *ghm = p.hm + (size_t)bin * p.A_pad;
+            if (use_pre) {
+                if (lane < nq_tile) tile4[lane] = pre;
+                if (b + 1 < nb && lane < nq_tile) pre = reinterpret_cast<const uint4 *>(ghm + p.A_pad)[lane];
+            } else {
+#pragma unroll 1
+                for (int k = lane; k < nq_tile; k += 32)
+                    tile4[k] = mode == kModeReset ? zero4 : reinterpret_cast<const uint4 *>(ghm)[k];
+            }
+#pragma unroll 1
+            for (int k = lane; k < nq_mask; k += 32) smask4[k] = zero4;
+            __syncwarp();
+
+            bool succ = false;
+            if (mode == kModeStep) {
+                if (bact >> 17) {
+                    const int bx = box & 0xff, by = (box >> 8) & 0xff, z = (box >> 16) & 0xff;
+                    const int lx = bact & 0xff, ly = (bact >> 8) & 0xff;
+                    const bool flag = (bact >> 16) & 1;
+                    const int x = flag ? by : bx, y = flag ? bx : by;           // space.py:166-172
+                    if (lx + x <= L && ly + y <= W) {                            // space.py:112-113
+                        // Space.check_box (space.py:116-144) with the lanes spread over the footprint
+                        uint8_t *w = tile + lx * W + ly;
+                        const int a = x * y;
+                        const uint32_t rcp = rcp16((uint32_t)y);
+                        const int c00 = w[0], c10 = w[(x - 1) * W], c01 = w[y - 1], c11 = w[(x - 1) * W + y - 1];
+                        int new_h;
+                        if (a <= 32) {
+                            const int r = (int)(((uint32_t)lane * rcp) >> 16), off = r * W + (lane - r * y);
+                            const int h = lane < a ? (int)w[off] : -1;
+                            const int m = __reduce_max_sync(kFull, h);
+                            const int cnt = __popc(__ballot_sync(kFull, h == m));
+                            new_h = accept<1>(m, cnt, make_thresholds(a), z, H, c00, c10, c01, c11);
+                            if (new_h >= 0) {                                    // update_height_graph, space.py:36-46
+                                __syncwarp();
+                                if (lane < a) w[off] = (uint8_t)(new_h + z);
+                            }
+                        } else {
+                            int m = -1;
+#pragma unroll 1
+                            for (int q = lane; q < a; q += 32) {
+                                const int r = (int)(((uint32_t)q * rcp) >> 16);
+                                m = max(m, (int)w[r * W + (q - r * y)]);
+                            }
+                            m = __reduce_max_sync(kFull, m);
+                            int cnt = 0;
+#pragma unroll 1
+                            for (int q = lane; q < a; q += 32) {
+                                const int r = (int)(((uint32_t)q * rcp) >> 16);
+                                cnt += (w[r * W + (q - r * y)] == m);
+                            }
+                            cnt = __reduce_add_sync(kFull, cnt);
+                            new_h = accept<1>(m, cnt, make_thresholds(a), z, H, c00, c10, c01, c11);
+                            if (new_h >= 0) {
+                                __syncwarp();
+#pragma unroll 1
+                                for (int q = lane; q < a; q += 32) {
+                                    const int r = (int)(((uint32_t)q * rcp) >> 16);
+                                    w[r * W + (q - r * y)] = (uint8_t)(new_h + z);
+                                }
+                            }
+                        }
+                        succ = new_h >= 0;
+                    }
+                }
+                if (!succ) {                                                     // auto-reset, shmem_vec_env.py:127-130
+                    __syncwarp();
+#pragma unroll 1
+                    for (int k = lane; k < nq_tile; k += 32) tile4[k] = zero4;  // Space(*bin_size), bin3D.py:57
+                }
+            }
+            const uint32_t nbox = mode == kModeObserve ? box : (succ ? b_ok : b_new);
+            __syncwarp();
+
+            // ground-truth mask of the new state
+            const int bx = nbox & 0xff, by = (nbox >> 8) & 0xff, bz = (nbox >> 16) & 0xff;
+            int total = 0;
+            if (io.mask || io.sample) {
+#pragma unroll 1
+                for (int o = 0; o < (ROT ? 2 : 1); ++o)
+                    total += sweep_orientation<VARIANT>(tile, smask + o * A, L, W, H, o ? by : bx, o ? bx : by, bz, lane);
+                __syncwarp();
+            }
+
+            // write back
+            if (mode != kModeObserve)
+#pragma unroll 1
+                for (int k = lane; k < nq_tile; k += 32) reinterpret_cast<uint4 *>(ghm)[k] = tile4[k];
+            if (io.obs) {                                                        // cur_observation, bin3D.py:61-66
+                float *o = io.obs + (size_t)bin * 4 * A;
+                const float fx = (float)bx, fy = (float)by, fz = (float)bz;
+                if (VEC4) {
+                    const int q4 = A >> 2;
+                    float4 *o4 = reinterpret_cast<float4 *>(o);
+                    const uint32_t *t32 = reinterpret_cast<const uint32_t *>(tile);
+#pragma unroll 1
+                    for (int k = lane; k < q4; k += 32) {
+                        __stcs(o4 + k, bytes_to_float4(t32[k]));
+                        __stcs(o4 + q4 + k, make_float4(fx, fx, fx, fx));
+                        __stcs(o4 + 2 * q4 + k, make_float4(fy, fy, fy, fy));
+                        __stcs(o4 + 3 * q4 + k, make_float4(fz, fz, fz, fz));
+                    }
+                } else {
+#pragma unroll 1
+                    for (int k = lane; k < A; k += 32) {
+                        __stcs(o + k, (float)tile[k]); __stcs(o + A + k, fx);
+                        __stcs(o + 2 * A + k, fy); __stcs(o + 3 * A + k, fz);
+                    }
+                }
+            }
+            if (io.mask) {                                                       // all-ones fallback, utils.py:59-60,89-92
+                float *mo = io.mask + (size_t)bin * p.M;
+                if (VEC4) {
+                    float4 *m4 = reinterpret_cast<float4 *>(mo);
+                    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(smask);
+#pragma unroll 1
+                    for (int k = lane; k < (p.M >> 2); k += 32)
+                        __stcs(m4 + k, total == 0 ? make_float4(1.f, 1.f, 1.f, 1.f) : bytes_to_float4(s32[k]));
+                } else {
+#pragma unroll 1
+                    for (int k = lane; k < p.M; k += 32) __stcs(mo + k, total == 0 ? 1.f : (float)smask[k]);
+                }
+            }
+            uint32_t pick = 0;
+            if (io.sample) {   // uniform over mask == 1 (over all M entries under the fallback)
+                if (total == 0) {
+                    pick = __umulhi(b_us, (uint32_t)p.M);
+                } else {
+                    int r = (int)__umulhi(b_us, (uint32_t)total);
+#pragma unroll 1
+                    for (int c0 = 0; c0 < p.M; c0 += 32) {
+                        const bool bit = (c0 + lane < p.M) && smask[c0 + lane];
+                        const unsigned bal = __ballot_sync(kFull, bit);
+                        const int n = __popc(bal);
+                        if (r < n) {
+                            const int rank = __popc(bal & ((1u << lane) - 1u));
+                            const unsigned sel = __ballot_sync(kFull, bit && rank == r);
+                            pick = (uint32_t)(c0 + __ffs(sel) - 1);
+                            break;
+                        }
+                        r -= n;
+                    }
+                }
+            }
+            if (lane == b) my_res = pick | (succ ? 0x80000000u : 0u);
             __syncwarp();
         }
 
-        // ---- 4. write back ---------------------------------------------------------------------------
-        if (mode != kModeObserve) {
-            uint4 *g = reinterpret_cast<uint4 *>(p.hm + (size_t)bin * p.A_pad);
-            for (int k = lane; k < p.A_pad / 16; k += 32) g[k] = tile4[k];
-            if (lane == 0) {
-                uint4 *sp = reinterpret_cast<uint4 *>(p.sc + bin);
-                sp[0] = make_uint4(s.box, (uint32_t)s.cnt, (uint32_t)s.vol, s.episode);
-                sp[1] = make_uint4(s.ctr + 1u, (uint32_t)s.pos, (uint32_t)s.ep_len, s.traj);
+        // ---- phase A2: lane = bin ---------------------------------------------------------------------
+        if (mode == kModeObserve) continue;
+        const bool succ = my_res >> 31;
+        bool finished = false;
+        if (mode == kModeStep) {
+            // reward = 10*v/LWH and ratio = vol/LWH: the reference divides in float64 and VecPyTorch rounds
+            // to float32 (bin3D.py:44-46,121; space.py:146-151; acktr/envs.py:192).  10*v, vol and LWH are
+            // integers < 2^24, so one IEEE float32 division gives the same float32 (no double rounding can
+            // cross a float32 midpoint: tests/test_oracle_golden.py::test_f32_division_equals_reference_route).
+            float reward = 0.f;
+            if (succ) {                                                          // bin3D.py:114-127
+                const int v = (int)(s.box & 0xff) * (int)((s.box >> 8) & 0xff) * (int)((s.box >> 16) & 0xff);
+                s.cnt += 1; s.vol += v; s.pos += 1;
+                reward = __fdiv_rn((float)(10 * v), p.lwh_f);
+            }
+            finished = have && !succ;                                            // bin3D.py:108-112
+            if (have) {
+                if (io.reward) io.reward[mybin] = reward;
+                if (io.done) io.done[mybin] = succ ? 0 : 1;
+                if (io.counter) io.counter[mybin] = s.cnt;
+                if (io.ratio) io.ratio[mybin] = __fdiv_rn((float)s.vol, p.lwh_f);
+            }
+            const unsigned fin = __ballot_sync(kFull, finished);
+            if (fin) {
+                m_ep += (unsigned long long)__popc(fin);
+                m_cnt += (unsigned long long)__reduce_add_sync(kFull, finished ? s.cnt : 0);
+                m_vol += (unsigned long long)__reduce_add_sync(kFull, finished ? s.vol : 0);
             }
         }
-        if (io.obs) {                                                        // cur_observation, bin3D.py:61-66
-            float *o = io.obs + (size_t)bin * 4 * A;
-            const float fx = (float)bx, fy = (float)by, fz = (float)bz;
-            if (VEC4) {
-                const int q4 = A >> 2;
-                float4 *o4 = reinterpret_cast<float4 *>(o);
-                const uint32_t *t32 = reinterpret_cast<const uint32_t *>(tile);
-                for (int k = lane; k < q4; k += 32) __stcs(o4 + k, bytes_to_float4(t32[k]));
-                for (int k = lane; k < q4; k += 32) __stcs(o4 + q4 + k, make_float4(fx, fx, fx, fx));
-                for (int k = lane; k < q4; k += 32) __stcs(o4 + 2 * q4 + k, make_float4(fy, fy, fy, fy));
-                for (int k = lane; k < q4; k += 32) __stcs(o4 + 3 * q4 + k, make_float4(fz, fz, fz, fz));
+        if (have) {
+            if (mode == kModeReset || finished) {                                // PackingGame.reset, bin3D.py:55-59
+                if (!fresh_reset) s.episode += 1;
+                s.cnt = 0; s.vol = 0; s.pos = 0; s.traj = traj_new;
+                s.box = next_new;
             } else {
-                for (int k = lane; k < A; k += 32) {
-                    __stcs(o + k, (float)tile[k]); __stcs(o + A + k, fx);
-                    __stcs(o + 2 * A + k, fy); __stcs(o + 3 * A + k, fz);
-                }
+                s.box = next_ok;
             }
+            if (io.sample) io.sample[mybin] = (long long)(my_res & 0x7fffffffu);
+            uint4 *sp = reinterpret_cast<uint4 *>(p.sc + mybin);
+            sp[0] = make_uint4(s.box, (uint32_t)s.cnt, (uint32_t)s.vol, s.episode);
+            sp[1] = make_uint4(s.ctr + 1u, (uint32_t)s.pos, (uint32_t)s.ep_len, s.traj);
         }
-        if (io.mask) {                                                       // all-ones fallback, utils.py:59-60,89-92
-            float *mo = io.mask + (size_t)bin * p.M;
-            if (VEC4) {
-                float4 *m4 = reinterpret_cast<float4 *>(mo);
-                const uint32_t *s32 = reinterpret_cast<const uint32_t *>(smask);
-                for (int k = lane; k < (p.M >> 2); k += 32)
-                    __stcs(m4 + k, total == 0 ? make_float4(1.f, 1.f, 1.f, 1.f) : bytes_to_float4(s32[k]));
-            } else {
-                for (int k = lane; k < p.M; k += 32) __stcs(mo + k, total == 0 ? 1.f : (float)smask[k]);
-            }
-        }
-        if (io.sample) {   // uniform over mask == 1 (over all M entries under the fallback)
-            const uint32_t u = draw(p.seed_lo, p.seed_hi, kDomSample, 0, gid, s.ctr);
-            long long pick;
-            if (total == 0) {
-                pick = (long long)__umulhi(u, (uint32_t)p.M);
-            } else {
-                int r = (int)__umulhi(u, (uint32_t)total);
-                pick = -1;
-                for (int c0 = 0; c0 < p.M; c0 += 32) {
-                    const bool bit = (c0 + lane < p.M) && smask[c0 + lane];
-                    const unsigned b = __ballot_sync(kFull, bit);
-                    const int n = __popc(b);
-                    if (r < n) {
-                        const int rank = __popc(b & ((1u << lane) - 1u));
-                        const unsigned sel = __ballot_sync(kFull, bit && rank == r);
-                        pick = c0 + __ffs(sel) - 1;
-                        break;
-                    }
-                    r -= n;
-                }
-            }
-            if (lane == 0) io.sample[bin] = pick;
-        }
-        __syncwarp();
     }
 
     // ---- episode metrics: registers -> shared -> one global atomic triple per CTA -------------------

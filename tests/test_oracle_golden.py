@@ -161,3 +161,23 @@ def test_edge_actions_and_sizes():
     env2.reset()
     env2.step([100, -5])
     assert env2.done.tolist() == [1, 1]
+
+
+def test_f32_division_equals_reference_route():
+    """The CUDA kernel computes reward = fdiv_rn(float(10*v), float(LWH)) and ratio = fdiv_rn(float(vol), float(LWH));
+    the reference computes float32(float64(v)/float64(LWH)*10.0) and float32(float64(vol)/float64(LWH))
+    (bin3D.py:44-46,121, space.py:146-151, acktr/envs.py:192).  Both routes give the same float32."""
+    rng = np.random.default_rng(0)
+    sizes = [1000, 8000, 864, 378, 125, 27000, 32 * 32 * 255, 7 * 11 * 13, 1]
+    sizes += [int(a) * int(b) * int(c) for a, b, c in rng.integers(1, 33, (40, 3))]
+    for lwh in sizes:
+        v = np.arange(0, lwh + 1, dtype=np.int64)
+        if len(v) > 300000:
+            v = np.unique(np.concatenate([v[:50000], rng.integers(0, lwh + 1, 200000)]))
+        ref_reward = ((v.astype(np.float64) / np.float64(lwh)) * 10.0).astype(np.float32)
+        ref_ratio = (v.astype(np.float64) / np.float64(lwh)).astype(np.float32)
+        ok = 10 * v < 2 ** 24
+        got_reward = (10 * v[ok]).astype(np.float32) / np.float32(lwh)
+        got_ratio = v.astype(np.float32) / np.float32(lwh)
+        assert got_reward.dtype == np.float32 and np.array_equal(got_reward, ref_reward[ok]), lwh
+        assert np.array_equal(got_ratio, ref_ratio), lwh
