@@ -101,32 +101,26 @@ __device__ __forceinline__ uint32_t rcp16(uint32_t d) { return c_rcp16[d]; }
 // 20*ma > 17*a, 2*ma > a, i.e. ma >= floor(19a/20)+1, floor(17a/20)+1, floor(a/2)+1: three thresholds
 // that depend only on the footprint area and are computed once per orientation.
 // ---------------------------------------------------------------------------------------------------
-struct Thresholds {
-    int full, most, half;
-};
-__device__ __forceinline__ Thresholds make_thresholds(int a)
+// The three thresholds travel packed in one word: full | most << 10 | half << 20 (a <= 1024 keeps each < 1024).
+__device__ __forceinline__ uint32_t pack_thresholds(int a)
 {
-    Thresholds t;
-    t.full = (19 * a) / 20 + 1;
-    t.most = (17 * a) / 20 + 1;
-    t.half = a / 2 + 1;
-    return t;
+    return (uint32_t)((19 * a) / 20 + 1) | ((uint32_t)((17 * a) / 20 + 1) << 10) | ((uint32_t)(a / 2 + 1) << 20);
 }
 
 template <int VARIANT>
-__device__ __forceinline__ int accept(int m, int cnt, Thresholds t, int z, int H, int c00, int c10, int c01, int c11)
+__device__ __forceinline__ bool accept(int m, int cnt, uint32_t thr, int z, int H, int c00, int c10, int c01, int c11)
 {
-    if (m + z > H) return -1;                            // space.py:134-135, utils.py:20-21
-    const bool full = cnt >= t.full, most = cnt >= t.most, half = cnt >= t.half;
+    const bool fits = m + z <= H;                        // space.py:134-135, utils.py:20-21
+    const bool full = cnt >= (int)(thr & 1023u), most = cnt >= (int)((thr >> 10) & 1023u), half = cnt >= (int)(thr >> 20);
     if (VARIANT == 1) {                                  // space.py:118-125,137-142
         const int rm = max(max(c00, c10), max(c01, c11));
-        const int sc = (c00 == rm) + (c10 == rm) + (c01 == rm) + (c11 == rm);
-        if (sc < 3) return -1;
+        // corners equal to the corner maximum: each min(rm - c, 1) is 0 (equal) or 1 (below)
+        const int sc = 4 - (min(rm - c00, 1) + min(rm - c10, 1) + min(rm - c01, 1) + min(rm - c11, 1));
         const bool top = rm == m;
-        return (full || (top && sc == 3 && most) || (top && sc == 4 && half)) ? m : -1;
-    } else {                                             // utils.py:23-33
-        const int nc = (c00 == m) + (c10 == m) + (c01 == m) + (c11 == m);
-        return (full || (nc == 3 && most) || (nc == 4 && half)) ? m : -1;
+        return fits && sc >= 3 && (full || (top && sc == 3 && most) || (top && sc == 4 && half));
+    } else {                                             // utils.py:23-33 (corners equal to the window maximum)
+        const int nc = 4 - (min(m - c00, 1) + min(m - c10, 1) + min(m - c01, 1) + min(m - c11, 1));
+        return fits && (full || (nc == 3 && most) || (nc == 4 && half));
     }
 }
 
@@ -148,9 +142,11 @@ __device__ __forceinline__ void window_stats(const T *w, int W, int x, int y, in
     }
 }
 
-// Same for a compile-time footprint: all cells go to registers, max tree, then equality count.
+// Same for a compile-time footprint: all cells go to registers, max tree, then the cells below the max are
+// counted with min(m - h, 1); the four corners come out of the same registers.
 template <int X, int Y>
-__device__ __forceinline__ void window_stats_fixed(const uint8_t *w, int W, int &m, int &cnt)
+__device__ __forceinline__ void window_stats_fixed(const uint8_t *w, int W, int &m, int &cnt, int &c00, int &c10,
+                                                   int &c01, int &c11)
 {
     int h[X * Y];
 #pragma unroll
@@ -160,51 +156,54 @@ __device__ __forceinline__ void window_stats_fixed(const uint8_t *w, int W, int 
     m = h[0];
 #pragma unroll
     for (int k = 1; k < X * Y; ++k) m = max(m, h[k]);
-    int below = 0;                       // cells strictly below the max: min(m - h, 1) is 0 or 1
+    int below = 0;
 #pragma unroll
     for (int k = 0; k < X * Y; ++k) below += min(m - h[k], 1);
     cnt = X * Y - below;
+    c00 = h[0]; c01 = h[Y - 1]; c10 = h[(X - 1) * Y]; c11 = h[X * Y - 1];
 }
 
-// One thread evaluates one footprint on int32 heightmaps (batched check_box entry point).
+// One thread evaluates one footprint on int32 heightmaps (batched check_box entry point): max_h or -1.
 template <int VARIANT, typename T>
 __device__ __forceinline__ int check_window(const T *w, int W, int x, int y, int z, int H)
 {
     const int c00 = (int)w[0], c10 = (int)w[(x - 1) * W], c01 = (int)w[y - 1], c11 = (int)w[(x - 1) * W + y - 1];
     int m, cnt;
     window_stats<T>(w, W, x, y, m, cnt);
-    return accept<VARIANT>(m, cnt, make_thresholds(x * y), z, H, c00, c10, c01, c11);
+    return accept<VARIANT>(m, cnt, pack_thresholds(x * y), z, H, c00, c10, c01, c11) ? m : -1;
 }
 
-// (max, count) of the footprint with the window code unrolled for the reference's item range (1..5 per side,
+// Window statistics with the window code unrolled for the reference's item range (1..5 per side,
 // --item-size-range, acktr/arguments.py:30): `code` = (x-1)*5 + (y-1), or -1 for any other size.  The switch is
-// warp-uniform (one indirect branch per candidate position); only the window code is specialised so that
-// the instruction footprint stays inside the instruction cache.
-__device__ __forceinline__ void window_stats_switch(const uint8_t *w, int W, int x, int y, int code, int &m, int &cnt)
+// warp-uniform (one indirect branch per candidate position); only the window code is specialised so that the
+// instruction footprint stays inside the instruction cache.
+__device__ __forceinline__ void window_stats_switch(const uint8_t *w, int W, int x, int y, int code, int &m, int &cnt,
+                                                    int &c00, int &c10, int &c01, int &c11)
 {
-#define BPP_WS_CASE(X, Y) case ((X) - 1) * 5 + ((Y) - 1): window_stats_fixed<X, Y>(w, W, m, cnt); break;
+#define BPP_WS_CASE(X, Y) case ((X) - 1) * 5 + ((Y) - 1): window_stats_fixed<X, Y>(w, W, m, cnt, c00, c10, c01, c11); break;
 #define BPP_WS_ROW(X) BPP_WS_CASE(X, 1) BPP_WS_CASE(X, 2) BPP_WS_CASE(X, 3) BPP_WS_CASE(X, 4) BPP_WS_CASE(X, 5)
     switch (code) {
         BPP_WS_ROW(1) BPP_WS_ROW(2) BPP_WS_ROW(3) BPP_WS_ROW(4) BPP_WS_ROW(5)
-    default: window_stats<uint8_t>(w, W, x, y, m, cnt); break;
+    default:
+        c00 = w[0]; c10 = w[(x - 1) * W]; c01 = w[y - 1]; c11 = w[(x - 1) * W + y - 1];
+        window_stats<uint8_t>(w, W, x, y, m, cnt);
+        break;
     }
 #undef BPP_WS_ROW
 #undef BPP_WS_CASE
 }
 
-// Mask of one orientation: lanes sweep the (L-x+1)(W-y+1) candidate positions of the tile, set
-// smask[i*W+j] = 1 where feasible, and return the number of feasible positions (warp-uniform).
-// acktr/utils.py:54-57 / envs/bpp0/bin3D.py:85-88.  smask must be zero on entry.
+// Mask of one orientation: lanes sweep the (L-x+1)(W-y+1) candidate positions of the tile, write
+// smask[i*W+j] = feasible, and return the number of feasible positions (warp-uniform).
+// acktr/utils.py:54-57 / envs/bpp0/bin3D.py:85-88.  smask must be zero on entry; thr = pack_thresholds(x*y).
 template <int VARIANT>
 __device__ __forceinline__ int sweep_orientation(const uint8_t *tile, uint8_t *smask, int L, int W, int H,
-                                                 int x, int y, int z, int lane)
+                                                 int x, int y, int z, uint32_t thr, int lane)
 {
     if (x > L || y > W) return 0;                        // range(width - x + 1) empty, utils.py:54-55
     const int ni = L - x + 1, nj = W - y + 1;
     const int npos = ni * nj;
     const uint32_t rcp = rcp16((uint32_t)nj);
-    const Thresholds th = make_thresholds(x * y);
-    const int o10 = (x - 1) * W, o01 = y - 1;
     const int code = (x <= 5 && y <= 5) ? (x - 1) * 5 + (y - 1) : -1;
     int total = 0;
 #pragma unroll 1
@@ -213,13 +212,11 @@ __device__ __forceinline__ int sweep_orientation(const uint8_t *tile, uint8_t *s
         bool ok = false;
         if (q < npos) {
             const int i = (int)(((uint32_t)q * rcp) >> 16);
-            const int j = q - i * nj;
-            const uint8_t *w = tile + i * W + j;
-            const int c00 = w[0], c10 = w[o10], c01 = w[o01], c11 = w[o10 + o01];
-            int m, cnt;
-            window_stats_switch(w, W, x, y, code, m, cnt);
-            ok = accept<VARIANT>(m, cnt, th, z, H, c00, c10, c01, c11) >= 0;
-            if (ok) smask[i * W + j] = 1;
+            const int idx = i * (W - nj) + q;            // i*W + (q - i*nj)
+            int m, cnt, c00, c10, c01, c11;
+            window_stats_switch(tile + idx, W, x, y, code, m, cnt, c00, c10, c01, c11);
+            ok = accept<VARIANT>(m, cnt, thr, z, H, c00, c10, c01, c11);
+            smask[idx] = ok ? 1 : 0;
         }
         total += __popc(__ballot_sync(kFull, ok));
     }

@@ -35,9 +35,10 @@ __global__ void __launch_bounds__(kThreads) bpp_mask_kernel(const void *src, con
         __syncwarp();
         int total = 0;
         // a non-positive dimension has no reference behaviour (numpy raises); treat as no position
-        if (bx > 0 && by > 0) {
-            total = sweep_orientation<VARIANT>(tile, smask, L, W, H, bx, by, bz, lane);
-            if (ROT) total += sweep_orientation<VARIANT>(tile, smask + A, L, W, H, by, bx, bz, lane);
+        if (bx > 0 && by > 0 && bx <= 255 && by <= 255) {
+            const uint32_t thr = pack_thresholds(bx * by);
+            total = sweep_orientation<VARIANT>(tile, smask, L, W, H, bx, by, bz, thr, lane);
+            if (ROT) total += sweep_orientation<VARIANT>(tile, smask + A, L, W, H, by, bx, bz, thr, lane);
         }
         __syncwarp();
         float *mo = mask + (size_t)row * M;

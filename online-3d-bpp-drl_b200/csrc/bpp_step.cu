@@ -92,16 +92,22 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
         }
         if (fresh_reset) { s.episode = 0; s.ctr = 0; }
         // action decode, envs/bpp0/bin3D.py:100-105 (strict '>': action == A stays un-rotated and falls out
-        // of bounds; without rotation an action > A trips the reference's assert, here it is infeasible)
-        // and Space.idx_to_position, space.py:153-156.  act = lx | ly << 8 | flag << 16 | valid << 17
-        uint32_t act = 0;
+        // of bounds; without rotation an action > A trips the reference's assert, here it is infeasible),
+        // Space.idx_to_position (space.py:153-156), orientation (space.py:166-172) and the bounds test of
+        // check_box (space.py:112-115).  act = cell offset | x << 10 | y << 16 | in-bounds << 22
+        uint32_t act = 0, thr_cur = 0;
         if (mode == kModeStep) {
             long long idx = action;
-            uint32_t flag = 0;
-            if (idx > A) { if (ROT) { idx -= A; flag = 1; } else idx = -1; }
+            bool flag = false;
+            if (idx > A) { if (ROT) { idx -= A; flag = true; } else idx = -1; }
             if (idx >= 0 && idx < A) {
-                const uint32_t lx = ((uint32_t)idx * rcpW) >> 16, ly = (uint32_t)idx - lx * (uint32_t)W;
-                act = lx | (ly << 8) | (flag << 16) | (1u << 17);
+                const int bx = s.box & 0xff, by = (s.box >> 8) & 0xff;
+                const int x = flag ? by : bx, y = flag ? bx : by;
+                const int lx = (int)(((uint32_t)idx * rcpW) >> 16), ly = (int)idx - lx * W;
+                if (lx + x <= L && ly + y <= W) {
+                    act = (uint32_t)idx | ((uint32_t)x << 10) | ((uint32_t)y << 16) | (1u << 22);
+                    thr_cur = pack_thresholds(x * y);
+                }
             }
         }
         // Philox draws of this step (counter n = s.ctr): item stream (rs) and action-sampler stream
@@ -129,6 +135,8 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             }
             }
         }
+        const uint32_t thr_ok = pack_thresholds((int)(next_ok & 0xff) * (int)((next_ok >> 8) & 0xff));
+        const uint32_t thr_new = pack_thresholds((int)(next_new & 0xff) * (int)((next_new >> 8) & 0xff));
         if (have && io.sample) u_samp = draw(p.seed_lo, p.seed_hi, kDomSample, 0, gid, s.ctr);
         uint32_t my_res = 0;      // from phase B: bit 31 = placement succeeded, low bits = sampled action
 
@@ -144,6 +152,8 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             const uint32_t b_ok = __shfl_sync(kFull, next_ok, b);
             const uint32_t b_new = __shfl_sync(kFull, next_new, b);
             const uint32_t b_us = __shfl_sync(kFull, u_samp, b);
+            const uint32_t b_thr_cur = __shfl_sync(kFull, thr_cur, b);
+            const uint32_t b_thr_ok = __shfl_sync(kFull, thr_ok, b), b_thr_new = __shfl_sync(kFull, thr_new, b);
             uint8_t *ghm = p.hm + (size_t)bin * p.A_pad;
             if (use_pre) {
                 if (lane < nq_tile) tile4[lane] = pre;
@@ -159,54 +169,47 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
 
             bool succ = false;
             if (mode == kModeStep) {
-                if (bact >> 17) {
-                    const int bx = box & 0xff, by = (box >> 8) & 0xff, z = (box >> 16) & 0xff;
-                    const int lx = bact & 0xff, ly = (bact >> 8) & 0xff;
-                    const bool flag = (bact >> 16) & 1;
-                    const int x = flag ? by : bx, y = flag ? bx : by;           // space.py:166-172
-                    if (lx + x <= L && ly + y <= W) {                            // space.py:112-113
-                        // Space.check_box (space.py:116-144) with the lanes spread over the footprint
-                        uint8_t *w = tile + lx * W + ly;
-                        const int a = x * y;
-                        const uint32_t rcp = rcp16((uint32_t)y);
-                        const int c00 = w[0], c10 = w[(x - 1) * W], c01 = w[y - 1], c11 = w[(x - 1) * W + y - 1];
-                        int new_h;
-                        if (a <= 32) {
-                            const int r = (int)(((uint32_t)lane * rcp) >> 16), off = r * W + (lane - r * y);
-                            const int h = lane < a ? (int)w[off] : -1;
-                            const int m = __reduce_max_sync(kFull, h);
-                            const int cnt = __popc(__ballot_sync(kFull, h == m));
-                            new_h = accept<1>(m, cnt, make_thresholds(a), z, H, c00, c10, c01, c11);
-                            if (new_h >= 0) {                                    // update_height_graph, space.py:36-46
-                                __syncwarp();
-                                if (lane < a) w[off] = (uint8_t)(new_h + z);
-                            }
-                        } else {
-                            int m = -1;
+                if (bact >> 22) {
+                    // Space.check_box (space.py:116-144) with the lanes spread over the footprint
+                    const int x = (bact >> 10) & 63, y = (bact >> 16) & 63, z = (box >> 16) & 0xff;
+                    uint8_t *w = tile + (bact & 1023u);
+                    const int a = x * y;
+                    const uint32_t rcp = rcp16((uint32_t)y);
+                    const int c00 = w[0], c10 = w[(x - 1) * W], c01 = w[y - 1], c11 = w[(x - 1) * W + y - 1];
+                    if (a <= 32) {
+                        const int r = (int)(((uint32_t)lane * rcp) >> 16), off = r * (W - y) + lane;
+                        const int h = lane < a ? (int)w[off] : -1;
+                        const int m = __reduce_max_sync(kFull, h);
+                        const int cnt = __popc(__ballot_sync(kFull, h == m));
+                        succ = accept<1>(m, cnt, b_thr_cur, z, H, c00, c10, c01, c11);
+                        if (succ) {                                          // update_height_graph, space.py:36-46
+                            __syncwarp();
+                            if (lane < a) w[off] = (uint8_t)(m + z);
+                        }
+                    } else {
+                        int m = -1;
+#pragma unroll 1
+                        for (int q = lane; q < a; q += 32) {
+                            const int r = (int)(((uint32_t)q * rcp) >> 16);
+                            m = max(m, (int)w[r * (W - y) + q]);
+                        }
+                        m = __reduce_max_sync(kFull, m);
+                        int cnt = 0;
+#pragma unroll 1
+                        for (int q = lane; q < a; q += 32) {
+                            const int r = (int)(((uint32_t)q * rcp) >> 16);
+                            cnt += (w[r * (W - y) + q] == m);
+                        }
+                        cnt = __reduce_add_sync(kFull, cnt);
+                        succ = accept<1>(m, cnt, b_thr_cur, z, H, c00, c10, c01, c11);
+                        if (succ) {
+                            __syncwarp();
 #pragma unroll 1
                             for (int q = lane; q < a; q += 32) {
                                 const int r = (int)(((uint32_t)q * rcp) >> 16);
-                                m = max(m, (int)w[r * W + (q - r * y)]);
-                            }
-                            m = __reduce_max_sync(kFull, m);
-                            int cnt = 0;
-#pragma unroll 1
-                            for (int q = lane; q < a; q += 32) {
-                                const int r = (int)(((uint32_t)q * rcp) >> 16);
-                                cnt += (w[r * W + (q - r * y)] == m);
-                            }
-                            cnt = __reduce_add_sync(kFull, cnt);
-                            new_h = accept<1>(m, cnt, make_thresholds(a), z, H, c00, c10, c01, c11);
-                            if (new_h >= 0) {
-                                __syncwarp();
-#pragma unroll 1
-                                for (int q = lane; q < a; q += 32) {
-                                    const int r = (int)(((uint32_t)q * rcp) >> 16);
-                                    w[r * W + (q - r * y)] = (uint8_t)(new_h + z);
-                                }
+                                w[r * (W - y) + q] = (uint8_t)(m + z);
                             }
                         }
-                        succ = new_h >= 0;
                     }
                 }
                 if (!succ) {                                                     // auto-reset, shmem_vec_env.py:127-130
@@ -216,6 +219,8 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                 }
             }
             const uint32_t nbox = mode == kModeObserve ? box : (succ ? b_ok : b_new);
+            const uint32_t nthr = mode == kModeObserve ? pack_thresholds((int)(box & 0xff) * (int)((box >> 8) & 0xff))
+                                                       : (succ ? b_thr_ok : b_thr_new);
             __syncwarp();
 
             // ground-truth mask of the new state
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             if (io.mask || io.sample) {
 #pragma unroll 1
                 for (int o = 0; o < (ROT ? 2 : 1); ++o)
-                    total += sweep_orientation<VARIANT>(tile, smask + o * A, L, W, H, o ? by : bx, o ? bx : by, bz, lane);
+                    total += sweep_orientation<VARIANT>(tile, smask + o * A, L, W, H, o ? by : bx, o ? bx : by, bz, nthr, lane);
                 __syncwarp();
             }
 
