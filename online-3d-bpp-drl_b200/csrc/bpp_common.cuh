@@ -90,6 +90,14 @@ __device__ __forceinline__ uint32_t draw(uint32_t seed_lo, uint32_t seed_hi, uin
     return w == 0 ? o.x : (w == 1 ? o.y : (w == 2 ? o.z : o.w));
 }
 
+// Keeps a loop-invariant value in a register: ptxas otherwise re-derives such values (S2R, LDC, integer
+// arithmetic) inside the per-position loop to save registers, which costs issue slots in an issue-bound kernel.
+__device__ __forceinline__ int pinned(int v)
+{
+    asm volatile("" : "+r"(v));
+    return v;
+}
+
 // floor(q / d) == (q * c_rcp16[d]) >> 16 for q < 1024, 1 <= d <= 32  (c_rcp16[d] = ceil(2^16 / d))
 __constant__ uint32_t c_rcp16[kMaxSide + 1] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115, 2048};
 __device__ __forceinline__ uint32_t rcp16(uint32_t d) { return c_rcp16[d]; }
@@ -108,10 +116,11 @@ __device__ __forceinline__ uint32_t pack_thresholds(int a)
 }
 
 template <int VARIANT>
-__device__ __forceinline__ bool accept(int m, int cnt, uint32_t thr, int z, int H, int c00, int c10, int c01, int c11)
+__device__ __forceinline__ bool accept(int m, int cnt, int thr_full, int thr_most, int thr_half, int zmax, int c00,
+                                       int c10, int c01, int c11)
 {
-    const bool fits = m + z <= H;                        // space.py:134-135, utils.py:20-21
-    const bool full = cnt >= (int)(thr & 1023u), most = cnt >= (int)((thr >> 10) & 1023u), half = cnt >= (int)(thr >> 20);
+    const bool fits = m <= zmax;                         // max_h + z <= H, space.py:134-135, utils.py:20-21
+    const bool full = cnt >= thr_full, most = cnt >= thr_most, half = cnt >= thr_half;
     if (VARIANT == 1) {                                  // space.py:118-125,137-142
         const int rm = max(max(c00, c10), max(c01, c11));
         // corners equal to the corner maximum: each min(rm - c, 1) is 0 (equal) or 1 (below)
@@ -122,6 +131,13 @@ __device__ __forceinline__ bool accept(int m, int cnt, uint32_t thr, int z, int 
         const int nc = 4 - (min(m - c00, 1) + min(m - c10, 1) + min(m - c01, 1) + min(m - c11, 1));
         return fits && (full || (nc == 3 && most) || (nc == 4 && half));
     }
+}
+
+template <int VARIANT>
+__device__ __forceinline__ bool accept(int m, int cnt, uint32_t thr, int z, int H, int c00, int c10, int c01, int c11)
+{
+    return accept<VARIANT>(m, cnt, (int)(thr & 1023u), (int)((thr >> 10) & 1023u), (int)(thr >> 20), H - z, c00, c10,
+                           c01, c11);
 }
 
 // (max, number of cells equal to the max) of an x-by-y window; one pass, any size.
@@ -201,21 +217,25 @@ __device__ __forceinline__ int sweep_orientation(const uint8_t *tile, uint8_t *s
                                                  int x, int y, int z, uint32_t thr, int lane)
 {
     if (x > L || y > W) return 0;                        // range(width - x + 1) empty, utils.py:54-55
-    const int ni = L - x + 1, nj = W - y + 1;
-    const int npos = ni * nj;
-    const uint32_t rcp = rcp16((uint32_t)nj);
-    const int code = (x <= 5 && y <= 5) ? (x - 1) * 5 + (y - 1) : -1;
+    const int nj = W - y + 1;
+    const int npos = pinned((L - x + 1) * nj);
+    const int rcp = pinned((int)rcp16((uint32_t)nj));
+    const int dW = pinned(W - nj);
+    const int code = pinned((x <= 5 && y <= 5) ? (x - 1) * 5 + (y - 1) : -1);
+    const int thr_full = pinned((int)(thr & 1023u)), thr_most = pinned((int)((thr >> 10) & 1023u)),
+              thr_half = pinned((int)(thr >> 20));
+    const int zmax = pinned(H - z);                      // m + z <= H  <=>  m <= H - z
     int total = 0;
 #pragma unroll 1
     for (int p0 = 0; p0 < npos; p0 += 32) {
         const int q = p0 + lane;
         bool ok = false;
         if (q < npos) {
-            const int i = (int)(((uint32_t)q * rcp) >> 16);
-            const int idx = i * (W - nj) + q;            // i*W + (q - i*nj)
+            const int i = (int)(((uint32_t)q * (uint32_t)rcp) >> 16);
+            const int idx = i * dW + q;                  // i*W + (q - i*nj)
             int m, cnt, c00, c10, c01, c11;
             window_stats_switch(tile + idx, W, x, y, code, m, cnt, c00, c10, c01, c11);
-            ok = accept<VARIANT>(m, cnt, thr, z, H, c00, c10, c01, c11);
+            ok = accept<VARIANT>(m, cnt, thr_full, thr_most, thr_half, zmax, c00, c10, c01, c11);
             smask[idx] = ok ? 1 : 0;
         }
         total += __popc(__ballot_sync(kFull, ok));

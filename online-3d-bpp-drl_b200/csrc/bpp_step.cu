@@ -55,9 +55,9 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ unsigned long long blk_metrics[3];
 
-    const int lane = threadIdx.x & 31;
+    const int lane = pinned((int)(threadIdx.x & 31));
     const int warp = threadIdx.x >> 5;
-    uint8_t *tile = smem + (size_t)warp * (p.A_pad + p.M_pad);
+    uint8_t *tile = smem + pinned(warp * (p.A_pad + p.M_pad));
     uint8_t *smask = tile + p.A_pad;
     uint4 *tile4 = reinterpret_cast<uint4 *>(tile);
     uint4 *smask4 = reinterpret_cast<uint4 *>(smask);
