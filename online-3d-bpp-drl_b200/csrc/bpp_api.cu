@@ -51,7 +51,7 @@ struct bpp_env {
     bpp_config cfg;
     EnvParams p;
     int rot, variant;
-    int num_sms, blocks_per_sm[2];   // [vec4]
+    int num_sms;
     size_t smem;
     bool was_reset;
     unsigned long long steps;
@@ -191,11 +191,6 @@ int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
     p.hm = e->d_hm; p.sc = e->d_sc; p.metrics = e->d_metrics;
 
     e->smem = (size_t)kWarpsPerBlock * (p.A_pad + p.M_pad);
-    for (int v = 0; v < 2; ++v) {
-        int b = 0;
-        BPP_CREATE_CUDA(step_occupancy(e->rot, e->variant, v == 1, e->smem, &b));
-        e->blocks_per_sm[v] = b > 0 ? b : 1;
-    }
     *out = e;
     return BPP_OK;
 }
@@ -204,11 +199,7 @@ static int run_step(bpp_env *env, const StepIO &io, int mode, void *stream)
 {
     const EnvParams &p = env->p;
     const bool vec4 = (p.A % 4 == 0) && (!io.obs || aligned16(io.obs)) && (!io.mask || aligned16(io.mask));
-    // persistent CTAs: one wave of resident blocks, grid-stride over bins
-    const long long want = ((long long)p.N + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const long long cap = (long long)env->num_sms * env->blocks_per_sm[vec4 ? 1 : 0];
-    const int grid = (int)(want < cap ? want : cap);
-    BPP_CUDA(launch_step(p, io, mode, env->rot, env->variant, vec4, grid, env->smem, as_stream(stream)));
+    BPP_CUDA(launch_step(p, io, mode, env->rot, env->variant, vec4, env->num_sms, env->smem, as_stream(stream)));
     g_launches.fetch_add(1);
     return BPP_OK;
 }

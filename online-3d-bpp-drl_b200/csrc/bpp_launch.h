@@ -8,9 +8,8 @@
 namespace bpp {
 
 // bpp_step.cu
-cudaError_t launch_step(const EnvParams &p, const StepIO &io, int mode, int rot, int variant, bool vec4,
-                        int grid, size_t smem, cudaStream_t st);
-cudaError_t step_occupancy(int rot, int variant, bool vec4, size_t smem, int *blocks_per_sm);
+cudaError_t launch_step(const EnvParams &p, const StepIO &io, int mode, int rot, int variant, bool vec4, int num_sms,
+                        size_t smem, cudaStream_t st);
 
 // bpp_mask.cu
 cudaError_t launch_mask_from_obs(const float *obs, int n, int L, int W, int H, int rot, int variant, float *mask,

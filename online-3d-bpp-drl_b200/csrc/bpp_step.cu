@@ -49,20 +49,28 @@ __device__ __forceinline__ uint32_t episode_item(const EnvParams &p, long long b
 //                     sweep, tile / observation / mask write-back, action sampling; the per-bin scalars
 //                     arrive by warp shuffle from the lane that owns the bin;
 //   A2 (lane = bin)   reward, done, info, new state record, coalesced stores, episode metrics.
-template <int ROT, int VARIANT, bool VEC4>
-__global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(const EnvParams p, const StepIO io, const int mode)
+//
+// Template parameters: ROT = enable_rotation, VARIANT = mask rule, VEC4 = 128-bit output stores possible,
+// CS = compile-time bin side (L == W == CS; 10 and 20 are the reference's configurations, 0 = any size read
+// from EnvParams), FAST = the rollout case (mode == step and every output requested) with the checks folded.
+template <int ROT, int VARIANT, bool VEC4, int CS, bool FAST>
+__global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(const EnvParams p, const StepIO io, const int mode_arg)
 {
+    const int mode = FAST ? (int)kModeStep : mode_arg;
+    const bool w_obs = FAST || io.obs != nullptr, w_mask = FAST || io.mask != nullptr, w_sample = FAST || io.sample != nullptr;
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ unsigned long long blk_metrics[3];
 
     const int lane = pinned((int)(threadIdx.x & 31));
     const int warp = threadIdx.x >> 5;
-    uint8_t *tile = smem + pinned(warp * (p.A_pad + p.M_pad));
-    uint8_t *smask = tile + p.A_pad;
+    const int L = CS ? CS : p.L, W = CS ? CS : p.W, H = p.H, A = CS ? CS * CS : p.A;
+    const int A_pad = CS ? ((CS * CS + 15) & ~15) : p.A_pad;
+    const int M = A * (ROT ? 2 : 1), M_pad = CS ? ((CS * CS * (ROT ? 2 : 1) + 15) & ~15) : p.M_pad;
+    uint8_t *tile = smem + pinned(warp * (A_pad + M_pad));
+    uint8_t *smask = tile + A_pad;
     uint4 *tile4 = reinterpret_cast<uint4 *>(tile);
     uint4 *smask4 = reinterpret_cast<uint4 *>(smask);
-    const int L = p.L, W = p.W, H = p.H, A = p.A;
-    const int nq_tile = p.A_pad >> 4, nq_mask = p.M_pad >> 4;     // 128-bit words per tile
+    const int nq_tile = A_pad >> 4, nq_mask = M_pad >> 4;     // 128-bit words per tile
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
     const uint32_t rcpW = rcp16((uint32_t)W);
     const bool fresh_reset = mode == kModeReset && !io.episode_inc;
@@ -137,13 +145,13 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
         }
         const uint32_t thr_ok = pack_thresholds((int)(next_ok & 0xff) * (int)((next_ok >> 8) & 0xff));
         const uint32_t thr_new = pack_thresholds((int)(next_new & 0xff) * (int)((next_new >> 8) & 0xff));
-        if (have && io.sample) u_samp = draw(p.seed_lo, p.seed_hi, kDomSample, 0, gid, s.ctr);
+        if (have && w_sample) u_samp = draw(p.seed_lo, p.seed_hi, kDomSample, 0, gid, s.ctr);
         uint32_t my_res = 0;      // from phase B: bit 31 = placement succeeded, low bits = sampled action
 
         // ---- phase B: warp = bin ----------------------------------------------------------------------
         uint4 pre = zero4;        // next bin's tile words, prefetched while the current bin is processed
         const bool use_pre = nq_tile <= 32 && mode != kModeReset;
-        if (use_pre && lane < nq_tile) pre = reinterpret_cast<const uint4 *>(p.hm + (size_t)bin0 * p.A_pad)[lane];
+        if (use_pre && lane < nq_tile) pre = reinterpret_cast<const uint4 *>(p.hm + (size_t)bin0 * A_pad)[lane];
 #pragma unroll 1
         for (int b = 0; b < nb; ++b) {
             const long long bin = bin0 + b;
@@ -154,10 +162,10 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             const uint32_t b_us = __shfl_sync(kFull, u_samp, b);
             const uint32_t b_thr_cur = __shfl_sync(kFull, thr_cur, b);
             const uint32_t b_thr_ok = __shfl_sync(kFull, thr_ok, b), b_thr_new = __shfl_sync(kFull, thr_new, b);
-            uint8_t *ghm = p.hm + (size_t)bin * p.A_pad;
+            uint8_t *ghm = p.hm + (size_t)bin * A_pad;
             if (use_pre) {
                 if (lane < nq_tile) tile4[lane] = pre;
-                if (b + 1 < nb && lane < nq_tile) pre = reinterpret_cast<const uint4 *>(ghm + p.A_pad)[lane];
+                if (b + 1 < nb && lane < nq_tile) pre = reinterpret_cast<const uint4 *>(ghm + A_pad)[lane];
             } else {
 #pragma unroll 1
                 for (int k = lane; k < nq_tile; k += 32)
@@ -226,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             // ground-truth mask of the new state
             const int bx = nbox & 0xff, by = (nbox >> 8) & 0xff, bz = (nbox >> 16) & 0xff;
             int total = 0;
-            if (io.mask || io.sample) {
+            if (w_mask || w_sample) {
 #pragma unroll 1
                 for (int o = 0; o < (ROT ? 2 : 1); ++o)
                     total += sweep_orientation<VARIANT>(tile, smask + o * A, L, W, H, o ? by : bx, o ? bx : by, bz, nthr, lane);
@@ -237,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             if (mode != kModeObserve)
 #pragma unroll 1
                 for (int k = lane; k < nq_tile; k += 32) reinterpret_cast<uint4 *>(ghm)[k] = tile4[k];
-            if (io.obs) {                                                        // cur_observation, bin3D.py:61-66
+            if (w_obs) {                                                        // cur_observation, bin3D.py:61-66
                 float *o = io.obs + (size_t)bin * 4 * A;
                 const float fx = (float)bx, fy = (float)by, fz = (float)bz;
                 if (VEC4) {
@@ -259,28 +267,28 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                     }
                 }
             }
-            if (io.mask) {                                                       // all-ones fallback, utils.py:59-60,89-92
-                float *mo = io.mask + (size_t)bin * p.M;
+            if (w_mask) {                                                       // all-ones fallback, utils.py:59-60,89-92
+                float *mo = io.mask + (size_t)bin * M;
                 if (VEC4) {
                     float4 *m4 = reinterpret_cast<float4 *>(mo);
                     const uint32_t *s32 = reinterpret_cast<const uint32_t *>(smask);
 #pragma unroll 1
-                    for (int k = lane; k < (p.M >> 2); k += 32)
+                    for (int k = lane; k < (M >> 2); k += 32)
                         __stcs(m4 + k, total == 0 ? make_float4(1.f, 1.f, 1.f, 1.f) : bytes_to_float4(s32[k]));
                 } else {
 #pragma unroll 1
-                    for (int k = lane; k < p.M; k += 32) __stcs(mo + k, total == 0 ? 1.f : (float)smask[k]);
+                    for (int k = lane; k < M; k += 32) __stcs(mo + k, total == 0 ? 1.f : (float)smask[k]);
                 }
             }
             uint32_t pick = 0;
-            if (io.sample) {   // uniform over mask == 1 (over all M entries under the fallback)
+            if (w_sample) {   // uniform over mask == 1 (over all M entries under the fallback)
                 if (total == 0) {
-                    pick = __umulhi(b_us, (uint32_t)p.M);
+                    pick = __umulhi(b_us, (uint32_t)M);
                 } else {
                     int r = (int)__umulhi(b_us, (uint32_t)total);
 #pragma unroll 1
-                    for (int c0 = 0; c0 < p.M; c0 += 32) {
-                        const bool bit = (c0 + lane < p.M) && smask[c0 + lane];
+                    for (int c0 = 0; c0 < M; c0 += 32) {
+                        const bool bit = (c0 + lane < M) && smask[c0 + lane];
                         const unsigned bal = __ballot_sync(kFull, bit);
                         const int n = __popc(bal);
                         if (r < n) {
@@ -314,10 +322,10 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             }
             finished = have && !succ;                                            // bin3D.py:108-112
             if (have) {
-                if (io.reward) io.reward[mybin] = reward;
-                if (io.done) io.done[mybin] = succ ? 0 : 1;
-                if (io.counter) io.counter[mybin] = s.cnt;
-                if (io.ratio) io.ratio[mybin] = __fdiv_rn((float)s.vol, p.lwh_f);
+                if (FAST || io.reward) io.reward[mybin] = reward;
+                if (FAST || io.done) io.done[mybin] = succ ? 0 : 1;
+                if (FAST || io.counter) io.counter[mybin] = s.cnt;
+                if (FAST || io.ratio) io.ratio[mybin] = __fdiv_rn((float)s.vol, p.lwh_f);
             }
             const unsigned fin = __ballot_sync(kFull, finished);
             if (fin) {
@@ -334,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             } else {
                 s.box = next_ok;
             }
-            if (io.sample) io.sample[mybin] = (long long)(my_res & 0x7fffffffu);
+            if (w_sample) io.sample[mybin] = (long long)(my_res & 0x7fffffffu);
             uint4 *sp = reinterpret_cast<uint4 *>(p.sc + mybin);
             sp[0] = make_uint4(s.box, (uint32_t)s.cnt, (uint32_t)s.vol, s.episode);
             sp[1] = make_uint4(s.ctr + 1u, (uint32_t)s.pos, (uint32_t)s.ep_len, s.traj);
@@ -351,38 +359,50 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
     }
 }
 
-template <int ROT, int VARIANT, bool VEC4>
-static cudaError_t launch_t(const EnvParams &p, const StepIO &io, int mode, int grid, size_t smem, cudaStream_t st)
+// One launch: persistent CTAs (one wave of resident blocks, grid-stride over 32-bin batches).
+template <int ROT, int VARIANT, bool VEC4, int CS, bool FAST>
+static cudaError_t launch_t(const EnvParams &p, const StepIO &io, int mode, int num_sms, size_t smem, cudaStream_t st)
 {
-    bpp_step_kernel<ROT, VARIANT, VEC4><<<grid, kThreads, smem, st>>>(p, io, mode);
+    static int blocks_per_sm[64] = {0};                 // per device
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    dev &= 63;
+    if (blocks_per_sm[dev] == 0) {
+        int b = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST>, kThreads, smem);
+        if (e != cudaSuccess) return e;
+        blocks_per_sm[dev] = b > 0 ? b : 1;
+    }
+    const long long batches = ((long long)p.N + 31) / 32;
+    const long long want = (batches + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const long long cap = (long long)num_sms * blocks_per_sm[dev];
+    const int grid = (int)(want < cap ? want : cap);
+    bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST><<<grid, kThreads, smem, st>>>(p, io, mode);
     return cudaGetLastError();
 }
 
-template <int ROT, int VARIANT, bool VEC4>
-static cudaError_t occupancy_t(int *blocks, size_t smem)
+template <int ROT, int VARIANT>
+static cudaError_t launch_rv(const EnvParams &p, const StepIO &io, int mode, bool vec4, int num_sms, size_t smem,
+                             cudaStream_t st)
 {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, bpp_step_kernel<ROT, VARIANT, VEC4>, kThreads, smem);
+    const bool fast = mode == kModeStep && io.obs && io.mask && io.reward && io.done && io.counter && io.ratio && io.sample;
+    const int cs = (vec4 && p.L == p.W && (p.L == 10 || p.L == 20)) ? p.L : 0;
+    if (cs == 10) return fast ? launch_t<ROT, VARIANT, true, 10, true>(p, io, mode, num_sms, smem, st)
+                              : launch_t<ROT, VARIANT, true, 10, false>(p, io, mode, num_sms, smem, st);
+    if (cs == 20) return fast ? launch_t<ROT, VARIANT, true, 20, true>(p, io, mode, num_sms, smem, st)
+                              : launch_t<ROT, VARIANT, true, 20, false>(p, io, mode, num_sms, smem, st);
+    return vec4 ? launch_t<ROT, VARIANT, true, 0, false>(p, io, mode, num_sms, smem, st)
+                : launch_t<ROT, VARIANT, false, 0, false>(p, io, mode, num_sms, smem, st);
 }
 
-#define BPP_DISPATCH(FN, ...)                                                         \
-    do {                                                                              \
-        if (rot) {                                                                    \
-            if (variant == 1) return vec4 ? FN<1, 1, true>(__VA_ARGS__) : FN<1, 1, false>(__VA_ARGS__); \
-            return vec4 ? FN<1, 2, true>(__VA_ARGS__) : FN<1, 2, false>(__VA_ARGS__);  \
-        }                                                                             \
-        if (variant == 1) return vec4 ? FN<0, 1, true>(__VA_ARGS__) : FN<0, 1, false>(__VA_ARGS__);     \
-        return vec4 ? FN<0, 2, true>(__VA_ARGS__) : FN<0, 2, false>(__VA_ARGS__);      \
-    } while (0)
-
-cudaError_t launch_step(const EnvParams &p, const StepIO &io, int mode, int rot, int variant, bool vec4,
-                        int grid, size_t smem, cudaStream_t st)
+cudaError_t launch_step(const EnvParams &p, const StepIO &io, int mode, int rot, int variant, bool vec4, int num_sms,
+                        size_t smem, cudaStream_t st)
 {
-    BPP_DISPATCH(launch_t, p, io, mode, grid, smem, st);
-}
-
-cudaError_t step_occupancy(int rot, int variant, bool vec4, size_t smem, int *blocks_per_sm)
-{
-    BPP_DISPATCH(occupancy_t, blocks_per_sm, smem);
+    if (rot) return variant == 1 ? launch_rv<1, 1>(p, io, mode, vec4, num_sms, smem, st)
+                                 : launch_rv<1, 2>(p, io, mode, vec4, num_sms, smem, st);
+    return variant == 1 ? launch_rv<0, 1>(p, io, mode, vec4, num_sms, smem, st)
+                        : launch_rv<0, 2>(p, io, mode, vec4, num_sms, smem, st);
 }
 
 }  // namespace bpp
