@@ -121,7 +121,7 @@ class ClockSampler(object):
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_oracle_rate(size, rot, gen, seed, budget_s, n_threads=0, bins=16384, steps=None, warmup=1):
+def cpu_oracle_rate(size, rot, gen, seed, budget_s, n_threads=0, bins=65536, steps=None, warmup=1):
     """Times the oracle (oracle/bpp_oracle.c, OpenMP) on a bounded sample of the workload."""
     import oracle as orc
     kw = gen_kwargs(gen)
@@ -132,8 +132,11 @@ def cpu_oracle_rate(size, rot, gen, seed, budget_s, n_threads=0, bins=16384, ste
         okw = dict(gen="rs")
     env = orc.OracleEnv(bins, size, rot=rot, seed=seed, n_threads=n_threads, **okw)
     env.reset()
-    for _ in range(warmup):
+    t_warm = time.perf_counter()
+    n_warm = 0
+    while n_warm < warmup or time.perf_counter() - t_warm < 1.5:     # OpenMP pool spin-up, page faults, clocks
         env.step(env.sample.copy())
+        n_warm += 1
     t0 = time.perf_counter()
     env.step(env.sample.copy())
     one = time.perf_counter() - t0
@@ -154,7 +157,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     bins, size, rot, gen, desc = WORKLOADS[args.workload]
-    sample_bins = min(bins, 16384)
+    sample_bins = min(bins, 65536)
     base, steps, dt = cpu_oracle_rate(size, rot, gen, args.seed, budget_s=0, bins=sample_bins,
                                       steps=args.steps, warmup=args.warmup)
     line = {

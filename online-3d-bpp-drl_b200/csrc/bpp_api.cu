@@ -66,6 +66,9 @@ struct bpp_env {
     float *d_reward, *d_ratio;
     uint8_t *d_done;
     int32_t *d_counter;
+    // worker streams / events for the chunk-pipelined host entry point
+    cudaStream_t ws[2];
+    cudaEvent_t ev_start, ev_done[2];
 };
 
 extern "C" {
@@ -81,6 +84,11 @@ int32_t bpp_destroy(bpp_env *env)
     cudaFree(env->d_hm); cudaFree(env->d_sc); cudaFree(env->d_items); cudaFree(env->d_traj);
     cudaFree(env->d_ep_items); cudaFree(env->d_traj_len); cudaFree(env->d_metrics); cudaFree(env->d_actions);
     cudaFree(env->d_reward); cudaFree(env->d_ratio); cudaFree(env->d_done); cudaFree(env->d_counter);
+    for (int k = 0; k < 2; ++k) {
+        if (env->ws[k]) cudaStreamDestroy(env->ws[k]);
+        if (env->ev_done[k]) cudaEventDestroy(env->ev_done[k]);
+    }
+    if (env->ev_start) cudaEventDestroy(env->ev_start);
     delete env;
     return BPP_OK;
 }
@@ -190,18 +198,43 @@ int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
     BPP_CREATE_CUDA(cudaMalloc(&e->d_counter, N * sizeof(int32_t)));
     p.hm = e->d_hm; p.sc = e->d_sc; p.metrics = e->d_metrics;
 
+    for (int k = 0; k < 2; ++k) {
+        BPP_CREATE_CUDA(cudaStreamCreateWithFlags(&e->ws[k], cudaStreamNonBlocking));
+        BPP_CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming));
+    }
+    BPP_CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming));
     e->smem = (size_t)kWarpsPerBlock * (p.A_pad + p.M_pad);
     *out = e;
     return BPP_OK;
 }
 
-static int run_step(bpp_env *env, const StepIO &io, int mode, void *stream)
+// Launches the step kernel over the bins [b0, b0 + n) of the env (the whole env when b0 = 0, n = N).
+static int run_step_range(bpp_env *env, const StepIO &io_all, int mode, long long b0, int n, cudaStream_t st)
 {
-    const EnvParams &p = env->p;
+    EnvParams p = env->p;
+    StepIO io = io_all;
+    p.N = n;
+    p.hm += (size_t)b0 * p.A_pad;
+    p.sc += b0;
+    p.global_offset += (unsigned long long)b0;
+    if (p.ep_items) p.ep_items += (size_t)b0 * p.ep_cap;
+    if (io.actions) io.actions += b0;
+    if (io.obs) io.obs += (size_t)b0 * 4 * p.A;
+    if (io.mask) io.mask += (size_t)b0 * p.M;
+    if (io.reward) io.reward += b0;
+    if (io.done) io.done += b0;
+    if (io.counter) io.counter += b0;
+    if (io.ratio) io.ratio += b0;
+    if (io.sample) io.sample += b0;
     const bool vec4 = (p.A % 4 == 0) && (!io.obs || aligned16(io.obs)) && (!io.mask || aligned16(io.mask));
-    BPP_CUDA(launch_step(p, io, mode, env->rot, env->variant, vec4, env->num_sms, env->smem, as_stream(stream)));
+    BPP_CUDA(launch_step(p, io, mode, env->rot, env->variant, vec4, env->num_sms, env->smem, st));
     g_launches.fetch_add(1);
     return BPP_OK;
+}
+
+static int run_step(bpp_env *env, const StepIO &io, int mode, void *stream)
+{
+    return run_step_range(env, io, mode, 0, env->p.N, as_stream(stream));
 }
 
 static int enter(bpp_env *env, const char *who)
@@ -244,8 +277,7 @@ int32_t bpp_step_host(bpp_env *env, const int64_t *actions_host, float *obs, flo
     if (!env->was_reset) return fail(BPP_ERR_STATE, "bpp_step_host: call bpp_reset first");
     if (!actions_host) return fail(BPP_ERR_INVALID, "bpp_step_host: actions_host is null");
     cudaStream_t st = as_stream(stream);
-    const size_t N = (size_t)env->p.N;
-    BPP_CUDA(cudaMemcpyAsync(env->d_actions, actions_host, N * sizeof(long long), cudaMemcpyHostToDevice, st));
+    const long long N = env->p.N;
     StepIO io{};
     io.actions = env->d_actions;
     io.obs = obs; io.mask = mask;
@@ -254,12 +286,29 @@ int32_t bpp_step_host(bpp_env *env, const int64_t *actions_host, float *obs, flo
     io.counter = counter_host ? env->d_counter : nullptr;
     io.ratio = ratio_host ? env->d_ratio : nullptr;
     io.sample = reinterpret_cast<long long *>(sample);
-    if (int rc = run_step(env, io, kModeStep, stream)) return rc;
+    // Chunk pipeline: bins are independent, so the env is stepped in up to 4 slices on two worker streams;
+    // slice c+1's action upload and slice c-1's result download overlap slice c's kernel.
+    const int chunks = N >= 131072 ? 4 : (N >= 32768 ? 2 : 1);
+    BPP_CUDA(cudaEventRecord(env->ev_start, st));
+    for (int k = 0; k < 2; ++k) BPP_CUDA(cudaStreamWaitEvent(env->ws[k], env->ev_start, 0));
+    for (int c = 0; c < chunks; ++c) {
+        const long long b0 = ((N * c / chunks) / 32) * 32;
+        const long long b1 = c + 1 == chunks ? N : ((N * (c + 1) / chunks) / 32) * 32;
+        const size_t n = (size_t)(b1 - b0);
+        if (n == 0) continue;
+        cudaStream_t w = env->ws[c & 1];
+        BPP_CUDA(cudaMemcpyAsync(env->d_actions + b0, actions_host + b0, n * sizeof(long long), cudaMemcpyHostToDevice, w));
+        if (int rc = run_step_range(env, io, kModeStep, b0, (int)n, w)) return rc;
+        if (reward_host) BPP_CUDA(cudaMemcpyAsync(reward_host + b0, env->d_reward + b0, n * sizeof(float), cudaMemcpyDeviceToHost, w));
+        if (done_host) BPP_CUDA(cudaMemcpyAsync(done_host + b0, env->d_done + b0, n, cudaMemcpyDeviceToHost, w));
+        if (counter_host) BPP_CUDA(cudaMemcpyAsync(counter_host + b0, env->d_counter + b0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, w));
+        if (ratio_host) BPP_CUDA(cudaMemcpyAsync(ratio_host + b0, env->d_ratio + b0, n * sizeof(float), cudaMemcpyDeviceToHost, w));
+    }
+    for (int k = 0; k < 2; ++k) {
+        BPP_CUDA(cudaEventRecord(env->ev_done[k], env->ws[k]));
+        BPP_CUDA(cudaStreamWaitEvent(st, env->ev_done[k], 0));
+    }
     env->steps += (unsigned long long)N;
-    if (reward_host) BPP_CUDA(cudaMemcpyAsync(reward_host, env->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (done_host) BPP_CUDA(cudaMemcpyAsync(done_host, env->d_done, N, cudaMemcpyDeviceToHost, st));
-    if (counter_host) BPP_CUDA(cudaMemcpyAsync(counter_host, env->d_counter, N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (ratio_host) BPP_CUDA(cudaMemcpyAsync(ratio_host, env->d_ratio, N * sizeof(float), cudaMemcpyDeviceToHost, st));
     BPP_CUDA(cudaStreamSynchronize(st));
     return BPP_OK;
 }

@@ -31,6 +31,7 @@ enum Mode : int { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
 
 struct EnvParams {
     int N, L, W, H, A, A_pad, M, M_pad;      // M = A * (1 + rot): mask length
+    int bpw_log2;                            // log2(bins per warp batch), chosen per launch
     int gen_kind;
     int n_items;
     const uint32_t *item_set;                // packed x | y<<8 | z<<16

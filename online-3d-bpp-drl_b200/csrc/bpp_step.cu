@@ -79,13 +79,16 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
     __syncthreads();
     unsigned long long m_ep = 0, m_cnt = 0, m_vol = 0;
 
-    const long long n_batches = ((long long)p.N + 31) >> 5;
+    // bins per warp batch: 32 when there are plenty of bins, fewer (power of two) for small N so that the
+    // batches still spread over all SMs instead of serialising 32 bins on a few warps
+    const int bpw_log2 = p.bpw_log2;
+    const long long n_batches = ((long long)p.N + (1 << bpw_log2) - 1) >> bpw_log2;
     for (long long batch = (long long)blockIdx.x * kWarpsPerBlock + warp; batch < n_batches;
          batch += (long long)gridDim.x * kWarpsPerBlock) {
-        const long long bin0 = batch << 5;
-        const long long mybin = bin0 + lane;
-        const bool have = mybin < p.N;
-        const int nb = (int)min(32ll, (long long)p.N - bin0);
+        const long long bin0 = batch << bpw_log2;
+        const int nb = (int)min((long long)(1 << bpw_log2), (long long)p.N - bin0);
+        const bool have = lane < nb;
+        const long long mybin = have ? bin0 + lane : bin0;
         const unsigned long long gid = p.global_offset + (unsigned long long)mybin;
 
         // ---- phase A: lane = bin ----------------------------------------------------------------------
@@ -374,11 +377,15 @@ static cudaError_t launch_t(const EnvParams &p, const StepIO &io, int mode, int 
         if (e != cudaSuccess) return e;
         blocks_per_sm[dev] = b > 0 ? b : 1;
     }
-    const long long batches = ((long long)p.N + 31) / 32;
-    const long long want = (batches + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const long long cap = (long long)num_sms * blocks_per_sm[dev];
+    // largest power-of-two batch (<= 32 bins per warp) that still gives every resident warp a batch
+    EnvParams q = p;
+    q.bpw_log2 = 5;
+    while (q.bpw_log2 > 0 && (((long long)p.N + (1 << q.bpw_log2) - 1) >> q.bpw_log2) < cap * kWarpsPerBlock) --q.bpw_log2;
+    const long long batches = ((long long)p.N + (1 << q.bpw_log2) - 1) >> q.bpw_log2;
+    const long long want = (batches + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int grid = (int)(want < cap ? want : cap);
-    bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST><<<grid, kThreads, smem, st>>>(p, io, mode);
+    bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST><<<grid, kThreads, smem, st>>>(q, io, mode);
     return cudaGetLastError();
 }
 
