@@ -41,6 +41,8 @@ WORKLOADS = {
     "cfg1": (4096, (10, 10, 10), False, "rs", "BASELINE configs[1]: 4096 bins, 10x10x10, rs"),
     "cfg2": (65536, (10, 10, 10), False, "cut2_replay", "BASELINE configs[2]: 65536 bins, 10x10x10, cut_2.pt replay"),
     "cfg3": (262144, (20, 20, 20), False, "rs", "BASELINE configs[3]: 262144 bins, 20x20x20, rs"),
+    "cut1": (65536, (10, 10, 10), False, "cut1", "65536 bins, 10x10x10, cut1 generator on device"),
+    "cut2": (65536, (10, 10, 10), False, "cut2", "65536 bins, 10x10x10, cut2 generator on device"),
     "cfg4": (65536, (10, 10, 10), True, "cut2_replay", "BASELINE configs[4]: 65536 bins per GPU (524288 over 8), rotation, cut_2 replay"),
 }
 
@@ -71,7 +73,7 @@ def gen_kwargs(gen):
     if gen == "cut2_replay":
         d = np.load(os.path.join(ROOT, "tests", "golden", "datasets.npz"))
         return dict(trajectories=(d["cut_2"], d["cut_2_len"]), first_traj=1)
-    return dict(data_type="rs")
+    return dict(data_type=gen)
 
 
 class ClockSampler(object):
@@ -129,7 +131,7 @@ def cpu_oracle_rate(size, rot, gen, seed, budget_s, n_threads=0, bins=65536, ste
         tr = kw.pop("trajectories")
         okw = dict(gen="replay", traj=tr[0], traj_len=tr[1], first_traj=kw.get("first_traj", 1))
     else:
-        okw = dict(gen="rs")
+        okw = dict(gen=gen)
     env = orc.OracleEnv(bins, size, rot=rot, seed=seed, n_threads=n_threads, **okw)
     env.reset()
     t_warm = time.perf_counter()

@@ -110,9 +110,12 @@ class BinPackingVecEnv(object):
             self._keep.append(items)
             cfg.n_items = items.shape[0]
             cfg.item_set_host = items.ctypes.data
-            for a in range(3):
-                cfg.lo[a] = int(items[0][a])                           # bin3D.py:25-30
-                cfg.hi[a] = int(items[-1][a])
+            if data_type == "cut2":                                    # given_bound = [box_set[0][0], box_set[-1][0]], bin3D.py:33
+                for a in range(3):
+                    cfg.lo[a], cfg.hi[a] = int(items[0][0]), int(items[-1][0])
+            else:                                                      # low = box_set[0], up = box_set[-1], bin3D.py:25-30
+                for a in range(3):
+                    cfg.lo[a], cfg.hi[a] = int(items[0][a]), int(items[-1][a])
         cfg.seed = int(seed)
         cfg.global_offset = int(global_offset)
         cfg.global_n = int(global_n if global_n is not None else self.num_envs)

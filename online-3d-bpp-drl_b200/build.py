@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "b200bpp", "libbpp_b200.so")
-SOURCES = ["bpp_api.cu", "bpp_step.cu", "bpp_mask.cu"]
+SOURCES = ["bpp_api.cu", "bpp_step.cu", "bpp_mask.cu", "bpp_gen.cu"]
 HEADERS = ["bpp_common.cuh", "bpp_launch.h", os.path.join("..", "..", "include", "bpp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]

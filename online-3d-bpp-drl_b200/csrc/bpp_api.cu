@@ -59,6 +59,8 @@ struct bpp_env {
     uint8_t *d_hm;
     BinScalars *d_sc;
     uint32_t *d_items, *d_traj, *d_ep_items;
+    int32_t *d_ep_len2;
+    uint8_t *d_gen_flag, *d_gen_scratch;
     int32_t *d_traj_len;
     unsigned long long *d_metrics;
     // staging for the host-buffer entry point
@@ -82,7 +84,8 @@ int32_t bpp_destroy(bpp_env *env)
     if (!env) return BPP_OK;
     cudaSetDevice(env->cfg.device);
     cudaFree(env->d_hm); cudaFree(env->d_sc); cudaFree(env->d_items); cudaFree(env->d_traj);
-    cudaFree(env->d_ep_items); cudaFree(env->d_traj_len); cudaFree(env->d_metrics); cudaFree(env->d_actions);
+    cudaFree(env->d_ep_items); cudaFree(env->d_ep_len2); cudaFree(env->d_gen_flag); cudaFree(env->d_gen_scratch);
+    cudaFree(env->d_traj_len); cudaFree(env->d_metrics); cudaFree(env->d_actions);
     cudaFree(env->d_reward); cudaFree(env->d_ratio); cudaFree(env->d_done); cudaFree(env->d_counter);
     for (int k = 0; k < 2; ++k) {
         if (env->ws[k]) cudaStreamDestroy(env->ws[k]);
@@ -179,9 +182,41 @@ int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
         p.gn_mod = (uint32_t)(global_n % T);
         break;
     }
+    case BPP_GEN_CUT1:
+    case BPP_GEN_CUT2: {
+        // cutCreator.py:69-76 asserts lo <= dim - lo for every cut (dim > hi), mdCreator.py:73-76 needs a cut that
+        // leaves both parts >= lo: both require hi + 1 >= 2 * lo.
+        const int axes = cfg->gen_kind == BPP_GEN_CUT1 ? 3 : 1;
+        int lo_min = 255;
+        for (int a = 0; a < axes; ++a) {
+            if (cfg->lo[a] < 1 || cfg->hi[a] < cfg->lo[a] || cfg->hi[a] > 255 || cfg->hi[a] + 1 < 2 * cfg->lo[a]) {
+                bpp_destroy(e);
+                return fail(BPP_ERR_INVALID, "bpp_create: cut generators need 1 <= lo <= hi and hi + 1 >= 2 * lo per axis");
+            }
+            lo_min = cfg->lo[a] < lo_min ? cfg->lo[a] : lo_min;
+        }
+        if ((cfg->L + cfg->W + cfg->H) / lo_min > 90) { bpp_destroy(e); return fail(BPP_ERR_INVALID, "bpp_create: bin too deep for the cut generators' split stack"); }
+        for (int a = 0; a < 3; ++a) { p.lo[a] = cfg->lo[axes == 3 ? a : 0]; p.hi[a] = cfg->hi[axes == 3 ? a : 0]; }
+        p.rot = e->rot;
+        const long long cap = (long long)(cfg->L / p.lo[0]) * (cfg->W / p.lo[1]) * (cfg->H / p.lo[2]);
+        if (cap < 1 || cap > 60000) { bpp_destroy(e); return fail(BPP_ERR_INVALID, "bpp_create: episode capacity out of range"); }
+        p.ep_cap = (int)cap;
+        p.ep_buf_bins = cfg->n_bins;
+        p.ep_bin0 = 0;
+        p.gen_scratch_stride = (long long)gen_scratch_bytes_per_bin(cfg->gen_kind, p.ep_cap);
+        const size_t Nb = (size_t)cfg->n_bins;
+        BPP_CREATE_CUDA(cudaMalloc(&e->d_ep_items, 2 * Nb * p.ep_cap * sizeof(uint32_t)));
+        BPP_CREATE_CUDA(cudaMalloc(&e->d_ep_len2, 2 * Nb * sizeof(int32_t)));
+        BPP_CREATE_CUDA(cudaMemset(e->d_ep_len2, 0, 2 * Nb * sizeof(int32_t)));
+        BPP_CREATE_CUDA(cudaMalloc(&e->d_gen_flag, Nb));
+        BPP_CREATE_CUDA(cudaMemset(e->d_gen_flag, 0, Nb));
+        BPP_CREATE_CUDA(cudaMalloc(&e->d_gen_scratch, Nb * (size_t)p.gen_scratch_stride));
+        p.ep_items = e->d_ep_items; p.ep_len2 = e->d_ep_len2; p.gen_flag = e->d_gen_flag; p.gen_scratch = e->d_gen_scratch;
+        break;
+    }
     default:
         bpp_destroy(e);
-        return fail(BPP_ERR_INVALID, "bpp_create: generator kind not available in this build (rs and replay are)");
+        return fail(BPP_ERR_INVALID, "bpp_create: unknown generator kind");
     }
 
     const size_t N = (size_t)p.N;
@@ -217,7 +252,8 @@ static int run_step_range(bpp_env *env, const StepIO &io_all, int mode, long lon
     p.hm += (size_t)b0 * p.A_pad;
     p.sc += b0;
     p.global_offset += (unsigned long long)b0;
-    if (p.ep_items) p.ep_items += (size_t)b0 * p.ep_cap;
+    if (p.gen_flag) p.gen_flag += b0;
+    p.ep_bin0 = b0;
     if (io.actions) io.actions += b0;
     if (io.obs) io.obs += (size_t)b0 * 4 * p.A;
     if (io.mask) io.mask += (size_t)b0 * p.M;
@@ -250,7 +286,16 @@ int32_t bpp_reset(bpp_env *env, float *obs, float *mask, int64_t *sample, void *
     StepIO io{};
     io.obs = obs; io.mask = mask; io.sample = reinterpret_cast<long long *>(sample);
     io.episode_inc = env->was_reset ? 1 : 0;
+    const bool cut = env->p.gen_kind >= 2;
+    if (cut && !env->was_reset) {                         // episodes 0 and 1 of every bin
+        BPP_CUDA(launch_gen(env->p, 0, 0u, as_stream(stream)));
+        g_launches.fetch_add(1);
+    }
     if (int rc = run_step(env, io, kModeReset, stream)) return rc;
+    if (cut && env->was_reset) {                          // every bin moved to its spare episode: refill
+        BPP_CUDA(launch_gen(env->p, 1, 0u, as_stream(stream)));
+        g_launches.fetch_add(1);
+    }
     env->was_reset = true;
     return BPP_OK;
 }
@@ -266,6 +311,10 @@ int32_t bpp_step(bpp_env *env, const int64_t *actions, float *obs, float *mask, 
     io.obs = obs; io.mask = mask; io.reward = reward; io.done = done; io.counter = counter; io.ratio = ratio;
     io.sample = reinterpret_cast<long long *>(sample);
     if (int rc = run_step(env, io, kModeStep, stream)) return rc;
+    if (env->p.gen_kind >= 2) {                           // refill the episode buffers of bins that just reset
+        BPP_CUDA(launch_gen(env->p, 1, 0u, as_stream(stream)));
+        g_launches.fetch_add(1);
+    }
     env->steps += (unsigned long long)env->p.N;
     return BPP_OK;
 }
@@ -307,6 +356,10 @@ int32_t bpp_step_host(bpp_env *env, const int64_t *actions_host, float *obs, flo
     for (int k = 0; k < 2; ++k) {
         BPP_CUDA(cudaEventRecord(env->ev_done[k], env->ws[k]));
         BPP_CUDA(cudaStreamWaitEvent(st, env->ev_done[k], 0));
+    }
+    if (env->p.gen_kind >= 2) {
+        BPP_CUDA(launch_gen(env->p, 1, 0u, st));
+        g_launches.fetch_add(1);
     }
     env->steps += (unsigned long long)N;
     BPP_CUDA(cudaStreamSynchronize(st));

@@ -23,7 +23,7 @@ struct __align__(16) BinScalars {
     uint32_t ctr;       // reset+step calls so far: Philox draw index
     int32_t pos;        // position inside the replayed / pre-cut episode
     int32_t ep_len;     // cut1/cut2: items in the current episode buffer
-    uint32_t traj;      // replay: trajectory row of the current episode
+    uint32_t traj;      // replay: trajectory row of the current episode; cut1/cut2: episode buffer being played (0/1)
 };
 static_assert(sizeof(BinScalars) == 32, "BinScalars must be one 32-byte sector");
 
@@ -44,8 +44,16 @@ struct EnvParams {
     float lwh_f;                             // L*W*H (< 2^24, exact in float32)
     uint8_t *hm;                             // [N][A_pad] heightmaps, uint8
     BinScalars *sc;                          // [N]
-    const uint32_t *ep_items;                // cut1/cut2: [N][ep_cap] packed items of the current episode
+    // cut1/cut2: two episode buffers per bin (the one being played and the pre-generated next one)
+    uint32_t *ep_items;                      // [2][ep_buf_bins][ep_cap] packed items
+    int32_t *ep_len2;                        // [2][ep_buf_bins] items per buffer
+    uint8_t *gen_flag;                       // [N] 1 = the spare buffer must be regenerated
+    uint8_t *gen_scratch;                    // [N][gen_scratch_stride] generator work space
     int ep_cap;
+    long long ep_buf_bins;                   // bins of the whole env (buffer stride), not of a launch slice
+    long long ep_bin0;                       // first bin of this launch slice inside the env
+    long long gen_scratch_stride;
+    int lo[3], hi[3], rot;                   // item range (cut1 per axis, cut2 lo[0]/hi[0]); enable_rotation
     unsigned long long *metrics;             // {episodes, sum counter, sum vol}
 };
 

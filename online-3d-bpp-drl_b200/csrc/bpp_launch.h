@@ -11,6 +11,10 @@ namespace bpp {
 cudaError_t launch_step(const EnvParams &p, const StepIO &io, int mode, int rot, int variant, bool vec4, int num_sms,
                         size_t smem, cudaStream_t st);
 
+// bpp_gen.cu
+cudaError_t launch_gen(const EnvParams &p, int mode, uint32_t e0, cudaStream_t st);
+size_t gen_scratch_bytes_per_bin(int gen_kind, int cap);
+
 // bpp_mask.cu
 cudaError_t launch_mask_from_obs(const float *obs, int n, int L, int W, int H, int rot, int variant, float *mask,
                                  int grid, cudaStream_t st);

@@ -35,10 +35,11 @@ __device__ __forceinline__ uint32_t replay_item(const EnvParams &p, uint32_t t, 
     return pos < __ldg(p.traj_len + t) ? __ldg(p.traj + (size_t)t * p.traj_cap + pos) : kSentinel10;
 }
 
-// Item at position `pos` of the bin's pre-cut episode (cut1: cutCreator.py:112-128, cut2: mdCreator.py:163-166).
-__device__ __forceinline__ uint32_t episode_item(const EnvParams &p, long long bin, int pos, int ep_len)
+// Item at position `pos` of one of the bin's two pre-cut episode buffers (cut1: cutCreator.py:112-128, sentinel
+// bin_size :113-115; cut2: mdCreator.py:163-166, sentinel (10,10,10) :161).
+__device__ __forceinline__ uint32_t episode_item(const EnvParams &p, long long bin, int buf, int pos, int ep_len)
 {
-    if (pos < ep_len) return __ldg(p.ep_items + (size_t)bin * p.ep_cap + pos);
+    if (pos < ep_len) return __ldg(p.ep_items + ((size_t)buf * p.ep_buf_bins + (size_t)(p.ep_bin0 + bin)) * p.ep_cap + pos);
     return p.gen_kind == 2 ? ((uint32_t)p.L | ((uint32_t)p.W << 8) | ((uint32_t)p.H << 16)) : kSentinel10;
 }
 
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
         uint32_t u_samp = 0;
         uint32_t next_ok = s.box, next_new = s.box;      // waiting item if the placement succeeds / a new episode starts
         uint32_t traj_new = s.traj;
+        int len_new = s.ep_len;
         if (have && mode != kModeObserve) {
             switch (p.gen_kind) {
             case 0: {   // rs: RandomBoxCreator.generate_box_size, envs/bpp0/binCreator.py:38-40 -- same draw either way
@@ -139,9 +141,12 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                 if (mode == kModeStep) next_ok = replay_item(p, s.traj, s.pos + 1);
                 break;
             }
-            default: {  // cut1 / cut2 episode buffers
-                next_new = episode_item(p, mybin, 0, s.ep_len);
-                if (mode == kModeStep) next_ok = episode_item(p, mybin, s.pos + 1, s.ep_len);
+            default: {  // cut1 / cut2: the episode being played and the pre-generated next one (bpp_gen.cu)
+                const int cur = fresh_reset ? 1 : (int)(s.traj & 1u);    // a fresh reset starts on buffer 0
+                traj_new = (uint32_t)(cur ^ 1);
+                len_new = __ldg(p.ep_len2 + (size_t)(cur ^ 1) * p.ep_buf_bins + (size_t)(p.ep_bin0 + mybin));
+                next_new = episode_item(p, mybin, cur ^ 1, 0, len_new);
+                if (mode == kModeStep) next_ok = episode_item(p, mybin, cur, s.pos + 1, s.ep_len);
                 break;
             }
             }
@@ -340,8 +345,9 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
         if (have) {
             if (mode == kModeReset || finished) {                                // PackingGame.reset, bin3D.py:55-59
                 if (!fresh_reset) s.episode += 1;
-                s.cnt = 0; s.vol = 0; s.pos = 0; s.traj = traj_new;
+                s.cnt = 0; s.vol = 0; s.pos = 0; s.traj = traj_new; s.ep_len = len_new;
                 s.box = next_new;
+                if (p.gen_kind >= 2 && !fresh_reset) p.gen_flag[mybin] = 1;  // refill the buffer just left (bpp_gen.cu)
             } else {
                 s.box = next_ok;
             }

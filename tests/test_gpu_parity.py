@@ -161,6 +161,32 @@ def test_config5_rotation_cut2_shard(env_mod, golden_dir):
                        T=96, seed=8, offset=3 * 65536, global_n=524288, edge_every=5)
 
 
+@pytest.mark.parametrize("kind", ["cut1", "cut2"])
+@pytest.mark.parametrize("rot", [False, True])
+def test_cut_generators_on_device(env_mod, kind, rot):
+    # episodes are cut on the device (bpp_gen.cu) with the oracle's Philox draw order
+    run_against_oracle(env_mod, 777, (10, 10, 10), rot, 2, dict(data_type=kind), T=60, seed=31, offset=5000, global_n=100000, edge_every=9)
+
+
+def test_cut_generators_20cube(env_mod):
+    run_against_oracle(env_mod, 96, (20, 20, 20), False, 2, dict(data_type="cut2"), T=80, seed=32)
+    run_against_oracle(env_mod, 96, (20, 20, 20), True, 1, dict(data_type="cut1"), T=80, seed=33)
+
+
+def test_cut_explicit_second_reset(env_mod):
+    # a second reset() moves every bin to its next episode (LoadBoxCreator-style index += 1), also for cut kinds
+    env = env_mod.BinPackingVecEnv(64, data_type="cut2", seed=4, want_sample=True)
+    o = orc.OracleEnv(64, gen="cut2", seed=4)
+    for _ in range(3):
+        env.reset(); o.reset()
+        assert np.array_equal(t2n(env.obs), o.obs) and np.array_equal(t2n(env.location_masks), o.mask)
+        for _ in range(5):
+            a = o.sample.copy()
+            import torch
+            env.step_device(torch.as_tensor(a, device="cuda")); o.step(a)
+            assert np.array_equal(t2n(env.obs), o.obs) and np.array_equal(t2n(env.done_t), o.done)
+
+
 def test_odd_sizes_scalar_store_path(env_mod):
     # L*W not a multiple of 4 -> scalar stores; non-square; big item set incl. items larger than the bin
     items = [(x, y, z) for x in (1, 3, 8) for y in (2, 7) for z in (1, 4)]
@@ -285,7 +311,7 @@ def test_errors_are_loud(env_mod):
     with pytest.raises(BppError):
         env_mod.BinPackingVecEnv(8, container_size=(40, 10, 10))
     with pytest.raises(BppError):
-        env_mod.BinPackingVecEnv(8, data_type="cut1")     # not in this build yet -> loud, no fallback
+        env_mod.BinPackingVecEnv(8, data_type="cut1", box_set=[(3, 3, 3), (4, 4, 4)])     # hi + 1 < 2 * lo: the reference asserts
 
 
 def test_full_size_properties(env_mod):
