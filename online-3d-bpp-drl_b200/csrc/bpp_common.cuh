@@ -106,6 +106,17 @@ __device__ __forceinline__ int pinned(int v)
     asm volatile("" : "+r"(v));
     return v;
 }
+__device__ __forceinline__ uint32_t pinned(uint32_t v)
+{
+    asm volatile("" : "+r"(v));
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T *pinned_ptr(T *ptr)      // global pointers only (the address space is forgotten)
+{
+    asm volatile("" : "+l"(ptr));
+    return ptr;
+}
 
 // floor(q / d) == (q * c_rcp16[d]) >> 16 for q < 1024, 1 <= d <= 32  (c_rcp16[d] = ceil(2^16 / d))
 __constant__ uint32_t c_rcp16[kMaxSide + 1] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115, 2048};

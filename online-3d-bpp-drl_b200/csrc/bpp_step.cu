@@ -61,8 +61,10 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
     const bool w_obs = FAST || io.obs != nullptr, w_mask = FAST || io.mask != nullptr, w_sample = FAST || io.sample != nullptr;
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ unsigned long long blk_metrics[3];
+    __shared__ float4 plane_lut[256];                 // (v, v, v, v) for the constant x / y / z planes of the observation
 
     const int lane = pinned((int)(threadIdx.x & 31));
+    __builtin_assume(lane >= 0 && lane < 32);
     const int warp = threadIdx.x >> 5;
     const int L = CS ? CS : p.L, W = CS ? CS : p.W, H = p.H, A = CS ? CS * CS : p.A;
     const int A_pad = CS ? ((CS * CS + 15) & ~15) : p.A_pad;
@@ -77,6 +79,10 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
     const bool fresh_reset = mode == kModeReset && !io.episode_inc;
 
     if (threadIdx.x < 3) blk_metrics[threadIdx.x] = 0ull;
+    {
+        const float f = (float)threadIdx.x;
+        plane_lut[threadIdx.x] = make_float4(f, f, f, f);
+    }
     __syncthreads();
     unsigned long long m_ep = 0, m_cnt = 0, m_vol = 0;
 
@@ -154,23 +160,28 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
         const uint32_t thr_ok = pack_thresholds((int)(next_ok & 0xff) * (int)((next_ok >> 8) & 0xff));
         const uint32_t thr_new = pack_thresholds((int)(next_new & 0xff) * (int)((next_new >> 8) & 0xff));
         if (have && w_sample) u_samp = draw(p.seed_lo, p.seed_hi, kDomSample, 0, gid, s.ctr);
+        // keep the per-lane results in registers: ptxas would otherwise re-derive them inside the 32-bin loop
+        act = pinned(act); thr_cur = pinned(thr_cur); next_ok = pinned(next_ok); next_new = pinned(next_new);
+        const uint32_t p_thr_ok = pinned(thr_ok), p_thr_new = pinned(thr_new);
+        uint8_t *hm0 = pinned_ptr(p.hm + (size_t)bin0 * A_pad);
+        float *obs0 = w_obs ? pinned_ptr(io.obs + (size_t)bin0 * 4 * A) : nullptr;
+        float *mask0 = w_mask ? pinned_ptr(io.mask + (size_t)bin0 * M) : nullptr;
         uint32_t my_res = 0;      // from phase B: bit 31 = placement succeeded, low bits = sampled action
 
         // ---- phase B: warp = bin ----------------------------------------------------------------------
         uint4 pre = zero4;        // next bin's tile words, prefetched while the current bin is processed
         const bool use_pre = nq_tile <= 32 && mode != kModeReset;
-        if (use_pre && lane < nq_tile) pre = reinterpret_cast<const uint4 *>(p.hm + (size_t)bin0 * A_pad)[lane];
+        if (use_pre && lane < nq_tile) pre = reinterpret_cast<const uint4 *>(hm0)[lane];
 #pragma unroll 1
         for (int b = 0; b < nb; ++b) {
-            const long long bin = bin0 + b;
             const uint32_t box = __shfl_sync(kFull, s.box, b);
             const uint32_t bact = __shfl_sync(kFull, act, b);
             const uint32_t b_ok = __shfl_sync(kFull, next_ok, b);
             const uint32_t b_new = __shfl_sync(kFull, next_new, b);
             const uint32_t b_us = __shfl_sync(kFull, u_samp, b);
             const uint32_t b_thr_cur = __shfl_sync(kFull, thr_cur, b);
-            const uint32_t b_thr_ok = __shfl_sync(kFull, thr_ok, b), b_thr_new = __shfl_sync(kFull, thr_new, b);
-            uint8_t *ghm = p.hm + (size_t)bin * A_pad;
+            const uint32_t b_thr_ok = __shfl_sync(kFull, p_thr_ok, b), b_thr_new = __shfl_sync(kFull, p_thr_new, b);
+            uint8_t *ghm = hm0 + (unsigned)b * (unsigned)A_pad;
             if (use_pre) {
                 if (lane < nq_tile) tile4[lane] = pre;
                 if (b + 1 < nb && lane < nq_tile) pre = reinterpret_cast<const uint4 *>(ghm + A_pad)[lane];
@@ -254,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
 #pragma unroll 1
                 for (int k = lane; k < nq_tile; k += 32) reinterpret_cast<uint4 *>(ghm)[k] = tile4[k];
             if (w_obs) {                                                        // cur_observation, bin3D.py:61-66
-                float *o = io.obs + (size_t)bin * 4 * A;
+                float *o = obs0 + (unsigned)b * (unsigned)(4 * A);
                 const float fx = (float)bx, fy = (float)by, fz = (float)bz;
                 if (VEC4) {
                     const int q4 = A >> 2;
@@ -263,9 +274,9 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
 #pragma unroll 1
                     for (int k = lane; k < q4; k += 32) {
                         __stcs(o4 + k, bytes_to_float4(t32[k]));
-                        __stcs(o4 + q4 + k, make_float4(fx, fx, fx, fx));
-                        __stcs(o4 + 2 * q4 + k, make_float4(fy, fy, fy, fy));
-                        __stcs(o4 + 3 * q4 + k, make_float4(fz, fz, fz, fz));
+                        __stcs(o4 + q4 + k, plane_lut[bx]);
+                        __stcs(o4 + 2 * q4 + k, plane_lut[by]);
+                        __stcs(o4 + 3 * q4 + k, plane_lut[bz]);
                     }
                 } else {
 #pragma unroll 1
@@ -276,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                 }
             }
             if (w_mask) {                                                       // all-ones fallback, utils.py:59-60,89-92
-                float *mo = io.mask + (size_t)bin * M;
+                float *mo = mask0 + (unsigned)b * (unsigned)M;
                 if (VEC4) {
                     float4 *m4 = reinterpret_cast<float4 *>(mo);
                     const uint32_t *s32 = reinterpret_cast<const uint32_t *>(smask);
