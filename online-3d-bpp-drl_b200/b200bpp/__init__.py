@@ -7,3 +7,4 @@ from ._cabi import BppError, MASK_V1, MASK_V2   # noqa: F401
 from .vec_env import BinPackingVecEnv, default_item_set   # noqa: F401
 from .envs import make_vec_envs   # noqa: F401
 from . import utils   # noqa: F401
+from .bpp0 import PackingGame   # noqa: F401,E402

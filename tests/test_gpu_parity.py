@@ -352,3 +352,47 @@ def test_full_size_properties(env_mod):
         m = env.metrics()
         assert m["episodes"] == ep and m["steps"] == N * T and m["sum_vol"] == vol_done
         env.close()
+
+
+def test_single_env_view_matches_golden(env_mod, golden_dir):
+    """PackingGame view (bin3D.py surface) replays a recorded reference trajectory: obs, reward, done, info, mask."""
+    import copy
+    from b200bpp.bpp0 import PackingGame, BoxCreator
+    g = np.load(os.path.join(golden_dir, "ref_rollouts_10_rot.npz"))
+    N = g["action"].shape[1]
+
+    class Scripted(BoxCreator):
+        def __init__(self, rows):
+            super().__init__()
+            self.rows, self.index, self.k = rows, -1, 0
+
+        def reset(self):
+            self.box_list.clear(); self.index += 1; self.k = 0
+
+        def generate_box_size(self, **kw):
+            row, n = self.rows[self.index]
+            self.box_list.append(tuple(int(v) for v in row[self.k]) if self.k < n else (10, 10, 10))
+            self.k += 1
+
+    for b in (0, 7):
+        rows = [(g["traj"][b + e * N], int(g["traj_len"][b + e * N])) for e in range(g["action"].shape[0] + 1)]
+        env = PackingGame(box_creator=Scripted(rows), container_size=(10, 10, 10), enable_rotation=True)
+        obs = env.reset()
+        for t in range(20):
+            assert np.array_equal(obs[:100], g["hm"][t, b]) and tuple(env.next_box) == tuple(g["box"][t, b])
+            clone = copy.deepcopy(env)                      # reorder.py:69,226,251 deep-copies the env
+            obs, r, d, info = env.step([int(g["action"][t, b])])
+            assert d == bool(g["done"][t, b]) and abs(r - g["reward"][t, b]) < 1e-9
+            assert info["counter"] == g["counter"][t, b] and abs(info["ratio"] - g["ratio"][t, b]) < 1e-9
+            assert np.array_equal(clone.space.plain.reshape(-1), g["hm"][t, b])   # the copy kept the old state
+            if d:
+                obs = env.reset()
+        env.close()
+    # env-side mask (v1) of the view == golden mask_v1 (no rotation)
+    g2 = np.load(os.path.join(golden_dir, "ref_rollouts_10_norot.npz"))
+    rows = [(g2["traj"][e * g2["action"].shape[1]], int(g2["traj_len"][e * g2["action"].shape[1]])) for e in range(4)]
+    env = PackingGame(box_creator=Scripted(rows), container_size=(10, 10, 10))
+    env.reset()
+    assert np.array_equal(env.get_possible_position().reshape(-1), g2["mask_v1"][0, 0])
+    assert env.space.get_action_space() == 100 and env.space.position_to_index((3, 4)) == 34
+    env.close()
