@@ -8,3 +8,4 @@ from .vec_env import BinPackingVecEnv, default_item_set   # noqa: F401
 from .envs import make_vec_envs   # noqa: F401
 from . import utils   # noqa: F401
 from .bpp0 import PackingGame   # noqa: F401,E402
+from . import rollout, dist   # noqa: F401,E402

@@ -139,17 +139,20 @@ template <int VARIANT>
 __device__ __forceinline__ bool accept(int m, int cnt, int thr_full, int thr_most, int thr_half, int zmax, int c00,
                                        int c10, int c01, int c11)
 {
+    // full implies most implies half (thresholds 0.95 > 0.85 > 0.50), so the three-way rule is one comparison of the
+    // count against the threshold selected by the number of corners below the reference height:
+    //   0 corners below -> half, 1 below -> most, otherwise -> full      (space.py:137-142, utils.py:28-33)
     const bool fits = m <= zmax;                         // max_h + z <= H, space.py:134-135, utils.py:20-21
-    const bool full = cnt >= thr_full, most = cnt >= thr_most, half = cnt >= thr_half;
-    if (VARIANT == 1) {                                  // space.py:118-125,137-142
+    if (VARIANT == 1) {                                  // corners against the corner maximum rm; needs rm == max_h
         const int rm = max(max(c00, c10), max(c01, c11));
-        // corners equal to the corner maximum: each min(rm - c, 1) is 0 (equal) or 1 (below)
-        const int sc = 4 - (min(rm - c00, 1) + min(rm - c10, 1) + min(rm - c01, 1) + min(rm - c11, 1));
+        const int below = min(rm - c00, 1) + min(rm - c10, 1) + min(rm - c01, 1) + min(rm - c11, 1);
         const bool top = rm == m;
-        return fits && sc >= 3 && (full || (top && sc == 3 && most) || (top && sc == 4 && half));
-    } else {                                             // utils.py:23-33 (corners equal to the window maximum)
-        const int nc = 4 - (min(m - c00, 1) + min(m - c10, 1) + min(m - c01, 1) + min(m - c11, 1));
-        return fits && (full || (nc == 3 && most) || (nc == 4 && half));
+        const int need = (top && below == 0) ? thr_half : ((top && below == 1) ? thr_most : thr_full);
+        return fits && below <= 1 && cnt >= need;        // sc = 4 - below >= 3, space.py:124-125
+    } else {                                             // corners against the window maximum
+        const int below = min(m - c00, 1) + min(m - c10, 1) + min(m - c01, 1) + min(m - c11, 1);
+        const int need = below == 0 ? thr_half : (below == 1 ? thr_most : thr_full);
+        return fits && cnt >= need;
     }
 }
 
@@ -218,12 +221,14 @@ __device__ __forceinline__ void window_stats_switch(const uint8_t *w, int W, int
 {
 #define BPP_WS_CASE(X, Y) case ((X) - 1) * 5 + ((Y) - 1): window_stats_fixed<X, Y>(w, W, m, cnt, c00, c10, c01, c11); break;
 #define BPP_WS_ROW(X) BPP_WS_CASE(X, 1) BPP_WS_CASE(X, 2) BPP_WS_CASE(X, 3) BPP_WS_CASE(X, 4) BPP_WS_CASE(X, 5)
-    switch (code) {
-        BPP_WS_ROW(1) BPP_WS_ROW(2) BPP_WS_ROW(3) BPP_WS_ROW(4) BPP_WS_ROW(5)
-    default:
+    if (code >= 0) {
+        switch (code) {
+            BPP_WS_ROW(1) BPP_WS_ROW(2) BPP_WS_ROW(3) BPP_WS_ROW(4) BPP_WS_ROW(5)
+        default: __builtin_unreachable();
+        }
+    } else {
         c00 = w[0]; c10 = w[(x - 1) * W]; c01 = w[y - 1]; c11 = w[(x - 1) * W + y - 1];
         window_stats<uint8_t>(w, W, x, y, m, cnt);
-        break;
     }
 #undef BPP_WS_ROW
 #undef BPP_WS_CASE

@@ -396,3 +396,28 @@ def test_single_env_view_matches_golden(env_mod, golden_dir):
     assert np.array_equal(env.get_possible_position().reshape(-1), g2["mask_v1"][0, 0])
     assert env.space.get_action_space() == 100 and env.space.position_to_index((3, 4)) == 34
     env.close()
+
+
+def test_device_rollout_glue(env_mod):
+    """main.py:148-174 on the device: storage shapes as acktr/storage.py, stats as Monitor, everything on the GPU."""
+    import torch
+    from b200bpp import rollout
+    env = env_mod.BinPackingVecEnv(2048, (10, 10, 10), enable_rotation=True, seed=6)
+    st = rollout.start(env, rollout.DeviceRolloutStorage(5, env))
+    stats = rollout.EpisodeStats(env)
+    torch.manual_seed(0)
+    for _ in range(6):
+        rollout.collect(env, st, stats=stats)
+        # every stored action was valid under the stored mask, every stored mask row has a feasible entry
+        assert bool((st.location_masks[:5].gather(2, st.actions) == 1).all())
+        assert bool((st.location_masks.sum(2) >= 1).all())
+        # masks[t+1] == 0 exactly where reward == 0 at t (a failed placement ends the episode)
+        assert torch.equal(st.masks[1:] == 0, st.rewards == 0)
+        st.after_update()
+    s = stats.read()
+    m = env.metrics()
+    assert s["episodes"] == m["episodes"] and abs(s["mean_ratio"] - m["sum_vol"] / m["episodes"] / 1000) < 1e-6
+    assert abs(s["mean_length"] - (m["sum_counter"] / m["episodes"] + 1)) < 1e-9
+    # with a valid-only policy episodes end only when nothing fits (all-ones fallback mask) or on the action==A quirk
+    assert s["mean_length"] > 5
+    env.close()
