@@ -238,7 +238,8 @@ int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
         BPP_CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming));
     }
     BPP_CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming));
-    e->smem = (size_t)kWarpsPerBlock * (p.A_pad + p.M_pad);
+    // per warp: heightmap tile + mask tile + 32 staged bin records of 80 bytes
+    e->smem = (size_t)kWarpsPerBlock * (p.A_pad + p.M_pad) + (size_t)kWarpsPerBlock * 32 * 80;
     *out = e;
     return BPP_OK;
 }

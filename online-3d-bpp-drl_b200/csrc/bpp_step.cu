@@ -27,6 +27,7 @@ __device__ __forceinline__ float4 bytes_to_float4(uint32_t w)
                        (float)(w >> 24));
 }
 
+constexpr int kRecQuads = 5;     // uint4 words per staged bin record
 constexpr uint32_t kSentinel10 = 10u | (10u << 8) | (10u << 16);   // binCreator.py:62,69-71; mdCreator.py:161
 
 // Item at position `pos` of replay trajectory `t` (LoadBoxCreator, envs/bpp0/binCreator.py:64-72).
@@ -71,6 +72,9 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
     const int M = A * (ROT ? 2 : 1), M_pad = CS ? ((CS * CS * (ROT ? 2 : 1) + 15) & ~15) : p.M_pad;
     uint8_t *tile = smem + pinned(warp * (A_pad + M_pad));
     uint8_t *smask = tile + A_pad;
+    // per-warp record of the 32 bins of a batch: 20 words per bin, written in phase A, read in B and A2, so that
+    // the per-lane scalars do not occupy registers during the tile work
+    uint4 *rec = reinterpret_cast<uint4 *>(smem + kWarpsPerBlock * (A_pad + M_pad)) + pinned(warp * (32 * kRecQuads));
     uint4 *tile4 = reinterpret_cast<uint4 *>(tile);
     uint4 *smask4 = reinterpret_cast<uint4 *>(smask);
     const int nq_tile = A_pad >> 4, nq_mask = M_pad >> 4;     // 128-bit words per tile
@@ -99,6 +103,7 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
         const unsigned long long gid = p.global_offset + (unsigned long long)mybin;
 
         // ---- phase A: lane = bin ----------------------------------------------------------------------
+        {
         BinScalars s = {};
         long long action = -1;
         if (have) {
@@ -160,13 +165,21 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
         const uint32_t thr_ok = pack_thresholds((int)(next_ok & 0xff) * (int)((next_ok >> 8) & 0xff));
         const uint32_t thr_new = pack_thresholds((int)(next_new & 0xff) * (int)((next_new >> 8) & 0xff));
         if (have && w_sample) u_samp = draw(p.seed_lo, p.seed_hi, kDomSample, 0, gid, s.ctr);
-        // keep the per-lane results in registers: ptxas would otherwise re-derive them inside the 32-bin loop
-        act = pinned(act); thr_cur = pinned(thr_cur); next_ok = pinned(next_ok); next_new = pinned(next_new);
-        const uint32_t p_thr_ok = pinned(thr_ok), p_thr_new = pinned(thr_new);
+        // stage the per-lane results: {box, act, thr_cur, next_ok} {next_new, thr_ok, thr_new, u_samp}
+        // {cnt, vol, episode, ctr} {pos, ep_len, traj, traj_new} {len_new, result, -, -}
+        {
+            uint4 *r = rec + lane * kRecQuads;
+            r[0] = make_uint4(s.box, act, thr_cur, next_ok);
+            r[1] = make_uint4(next_new, thr_ok, thr_new, u_samp);
+            r[2] = make_uint4((uint32_t)s.cnt, (uint32_t)s.vol, s.episode, s.ctr);
+            r[3] = make_uint4((uint32_t)s.pos, (uint32_t)s.ep_len, s.traj, traj_new);
+            r[4] = make_uint4((uint32_t)len_new, 0u, 0u, 0u);
+        }
+        }
+        __syncwarp();
         uint8_t *hm0 = pinned_ptr(p.hm + (size_t)bin0 * A_pad);
         float *obs0 = w_obs ? pinned_ptr(io.obs + (size_t)bin0 * 4 * A) : nullptr;
         float *mask0 = w_mask ? pinned_ptr(io.mask + (size_t)bin0 * M) : nullptr;
-        uint32_t my_res = 0;      // from phase B: bit 31 = placement succeeded, low bits = sampled action
 
         // ---- phase B: warp = bin ----------------------------------------------------------------------
         uint4 pre = zero4;        // next bin's tile words, prefetched while the current bin is processed
@@ -174,13 +187,9 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
         if (use_pre && lane < nq_tile) pre = reinterpret_cast<const uint4 *>(hm0)[lane];
 #pragma unroll 1
         for (int b = 0; b < nb; ++b) {
-            const uint32_t box = __shfl_sync(kFull, s.box, b);
-            const uint32_t bact = __shfl_sync(kFull, act, b);
-            const uint32_t b_ok = __shfl_sync(kFull, next_ok, b);
-            const uint32_t b_new = __shfl_sync(kFull, next_new, b);
-            const uint32_t b_us = __shfl_sync(kFull, u_samp, b);
-            const uint32_t b_thr_cur = __shfl_sync(kFull, thr_cur, b);
-            const uint32_t b_thr_ok = __shfl_sync(kFull, p_thr_ok, b), b_thr_new = __shfl_sync(kFull, p_thr_new, b);
+            const uint4 r0 = rec[b * kRecQuads], r1 = rec[b * kRecQuads + 1];      // broadcast reads
+            const uint32_t box = r0.x, bact = r0.y, b_thr_cur = r0.z, b_ok = r0.w;
+            const uint32_t b_new = r1.x, b_thr_ok = r1.y, b_thr_new = r1.z, b_us = r1.w;
             uint8_t *ghm = hm0 + (unsigned)b * (unsigned)A_pad;
             if (use_pre) {
                 if (lane < nq_tile) tile4[lane] = pre;
@@ -320,12 +329,23 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                     }
                 }
             }
-            if (lane == b) my_res = pick | (succ ? 0x80000000u : 0u);
+            if (lane == 0) reinterpret_cast<uint32_t *>(rec + b * kRecQuads + 4)[1] = pick | (succ ? 0x80000000u : 0u);
             __syncwarp();
         }
 
         // ---- phase A2: lane = bin ---------------------------------------------------------------------
         if (mode == kModeObserve) continue;
+        BinScalars s;
+        uint32_t next_ok, next_new, traj_new, my_res;
+        int len_new;
+        {
+            const uint4 *r = rec + lane * kRecQuads;
+            const uint4 a = r[0], b1 = r[1], c = r[2], d = r[3], e4 = r[4];
+            s.box = a.x; next_ok = a.w; next_new = b1.x;
+            s.cnt = (int)c.x; s.vol = (int)c.y; s.episode = c.z; s.ctr = c.w;
+            s.pos = (int)d.x; s.ep_len = (int)d.y; s.traj = d.z; traj_new = d.w;
+            len_new = (int)e4.x; my_res = e4.y;
+        }
         const bool succ = my_res >> 31;
         bool finished = false;
         if (mode == kModeStep) {
