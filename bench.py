@@ -263,12 +263,18 @@ def main():
     h_cnt = torch.empty((N,), dtype=torch.int32).pin_memory()
     h_rat = torch.empty((N,), dtype=torch.float32).pin_memory()
 
+    h_act2 = torch.empty((N,), dtype=torch.int64).pin_memory()
+    hbufs = [h_act, h_act2]
+
     def step_host(src, dst):
-        h_act.copy_(src, non_blocking=True)          # policy output leaves the device (acktr/envs.py:186)
-        stream.synchronize()
-        _cabi.check(lib.bpp_step_host(env._h, P(h_act), P(env.obs), P(env.location_masks), P(h_rew), P(h_done),
+        # actions come from pinned host memory; the env writes the next sampled action (the policy stand-in's
+        # output) straight into the other pinned buffer, i.e. the policy output also crosses PCIe every step
+        _cabi.check(lib.bpp_step_host(env._h, P(src), P(env.obs), P(env.location_masks), P(h_rew), P(h_done),
                                       P(h_cnt), P(h_rat), P(dst), sptr()))
 
+    hbufs[cur & 1].copy_(bufs[cur & 1])
+    torch.cuda.synchronize(dev)
+    bufs = hbufs
     for i in range(3):
         step_host(bufs[(cur + i) & 1], bufs[(cur + i + 1) & 1])
     cur = (cur + 3) & 1
@@ -316,8 +322,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "steps": e2e_steps,
                     "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": (8 + 4 + 1 + 4 + 4) * N,
                     "ms_per_step": max(e2e_ms, e2e_wall_ms) / e2e_steps,
-                    "api": "BinPackingVecEnv/bpp_step_host: pinned int64 actions H2D, reward/done/counter/ratio D2H, "
-                           "obs+mask stay on device (as acktr/envs.py:191); policy output D2H included"},
+                    "api": "bpp_step_host (the call under BinPackingVecEnv.step): int64 actions read from pinned host "
+                           "memory, reward/done/counter/ratio and the next sampled action written to pinned host memory "
+                           "(zero-copy over PCIe inside the kernel), stream synchronised every step; obs+mask stay on "
+                           "the device as in acktr/envs.py:191"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": tr, "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_alg,
