@@ -70,7 +70,8 @@ struct bpp_env {
     BinScalars *d_sc;
     uint32_t *d_items, *d_traj, *d_ep_items;
     int32_t *d_ep_len2;
-    uint8_t *d_gen_flag, *d_gen_scratch;
+    int32_t *d_gen_list, *d_gen_count;
+    uint8_t *d_gen_scratch;
     int32_t *d_traj_len;
     unsigned long long *d_metrics;
     // staging for the host-buffer entry point
@@ -98,7 +99,7 @@ int32_t bpp_destroy(bpp_env *env)
     if (!env) return BPP_OK;
     cudaSetDevice(env->cfg.device);
     cudaFree(env->d_hm); cudaFree(env->d_sc); cudaFree(env->d_items); cudaFree(env->d_traj);
-    cudaFree(env->d_ep_items); cudaFree(env->d_ep_len2); cudaFree(env->d_gen_flag); cudaFree(env->d_gen_scratch);
+    cudaFree(env->d_ep_items); cudaFree(env->d_ep_len2); cudaFree(env->d_gen_list); cudaFree(env->d_gen_count); cudaFree(env->d_gen_scratch);
     cudaFree(env->d_traj_len); cudaFree(env->d_metrics); cudaFree(env->d_actions);
     cudaFree(env->d_reward); cudaFree(env->d_ratio); cudaFree(env->d_done); cudaFree(env->d_counter);
     for (int k = 0; k < 2; ++k) {
@@ -222,10 +223,11 @@ int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
         BPP_CREATE_CUDA(cudaMalloc(&e->d_ep_items, 2 * Nb * p.ep_cap * sizeof(uint32_t)));
         BPP_CREATE_CUDA(cudaMalloc(&e->d_ep_len2, 2 * Nb * sizeof(int32_t)));
         BPP_CREATE_CUDA(cudaMemset(e->d_ep_len2, 0, 2 * Nb * sizeof(int32_t)));
-        BPP_CREATE_CUDA(cudaMalloc(&e->d_gen_flag, Nb));
-        BPP_CREATE_CUDA(cudaMemset(e->d_gen_flag, 0, Nb));
+        BPP_CREATE_CUDA(cudaMalloc(&e->d_gen_list, Nb * sizeof(int32_t)));
+        BPP_CREATE_CUDA(cudaMalloc(&e->d_gen_count, sizeof(int32_t)));
+        BPP_CREATE_CUDA(cudaMemset(e->d_gen_count, 0, sizeof(int32_t)));
         BPP_CREATE_CUDA(cudaMalloc(&e->d_gen_scratch, Nb * (size_t)p.gen_scratch_stride));
-        p.ep_items = e->d_ep_items; p.ep_len2 = e->d_ep_len2; p.gen_flag = e->d_gen_flag; p.gen_scratch = e->d_gen_scratch;
+        p.ep_items = e->d_ep_items; p.ep_len2 = e->d_ep_len2; p.gen_list = e->d_gen_list; p.gen_count = e->d_gen_count; p.gen_scratch = e->d_gen_scratch;
         break;
     }
     default:
@@ -267,7 +269,6 @@ static int run_step_range(bpp_env *env, const StepIO &io_all, int mode, long lon
     p.hm += (size_t)b0 * p.A_pad;
     p.sc += b0;
     p.global_offset += (unsigned long long)b0;
-    if (p.gen_flag) p.gen_flag += b0;
     p.ep_bin0 = b0;
     if (io.actions) io.actions += b0;
     if (io.obs) io.obs += (size_t)b0 * 4 * p.A;
@@ -303,12 +304,12 @@ int32_t bpp_reset(bpp_env *env, float *obs, float *mask, int64_t *sample, void *
     io.episode_inc = env->was_reset ? 1 : 0;
     const bool cut = env->p.gen_kind >= 2;
     if (cut && !env->was_reset) {                         // episodes 0 and 1 of every bin
-        BPP_CUDA(launch_gen(env->p, 0, 0u, as_stream(stream)));
+        BPP_CUDA(launch_gen(env->p, 0, 0u, env->num_sms, as_stream(stream)));
         g_launches.fetch_add(1);
     }
     if (int rc = run_step(env, io, kModeReset, stream)) return rc;
     if (cut && env->was_reset) {                          // every bin moved to its spare episode: refill
-        BPP_CUDA(launch_gen(env->p, 1, 0u, as_stream(stream)));
+        BPP_CUDA(launch_gen(env->p, 1, 0u, env->num_sms, as_stream(stream)));
         g_launches.fetch_add(1);
     }
     env->was_reset = true;
@@ -327,7 +328,7 @@ int32_t bpp_step(bpp_env *env, const int64_t *actions, float *obs, float *mask, 
     io.sample = reinterpret_cast<long long *>(sample);
     if (int rc = run_step(env, io, kModeStep, stream)) return rc;
     if (env->p.gen_kind >= 2) {                           // refill the episode buffers of bins that just reset
-        BPP_CUDA(launch_gen(env->p, 1, 0u, as_stream(stream)));
+        BPP_CUDA(launch_gen(env->p, 1, 0u, env->num_sms, as_stream(stream)));
         g_launches.fetch_add(1);
     }
     env->steps += (unsigned long long)env->p.N;
@@ -373,7 +374,7 @@ int32_t bpp_step_host(bpp_env *env, const int64_t *actions_host, float *obs, flo
             z.counter = static_cast<int32_t *>(env->zc_dev[4]);
             if (int rc = run_step(env, z, kModeStep, stream)) return rc;
             if (env->p.gen_kind >= 2) {
-                BPP_CUDA(launch_gen(env->p, 1, 0u, st));
+                BPP_CUDA(launch_gen(env->p, 1, 0u, env->num_sms, st));
                 g_launches.fetch_add(1);
             }
             env->steps += (unsigned long long)N;
@@ -404,7 +405,7 @@ int32_t bpp_step_host(bpp_env *env, const int64_t *actions_host, float *obs, flo
         BPP_CUDA(cudaStreamWaitEvent(st, env->ev_done[k], 0));
     }
     if (env->p.gen_kind >= 2) {
-        BPP_CUDA(launch_gen(env->p, 1, 0u, st));
+        BPP_CUDA(launch_gen(env->p, 1, 0u, env->num_sms, st));
         g_launches.fetch_add(1);
     }
     env->steps += (unsigned long long)N;

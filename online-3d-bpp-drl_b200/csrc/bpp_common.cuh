@@ -47,7 +47,8 @@ struct EnvParams {
     // cut1/cut2: two episode buffers per bin (the one being played and the pre-generated next one)
     uint32_t *ep_items;                      // [2][ep_buf_bins][ep_cap] packed items
     int32_t *ep_len2;                        // [2][ep_buf_bins] items per buffer
-    uint8_t *gen_flag;                       // [N] 1 = the spare buffer must be regenerated
+    int32_t *gen_list;                       // [ep_buf_bins] env-wide ids of bins whose spare buffer must be regenerated
+    int32_t *gen_count;                      // number of entries in gen_list (appended by the step kernel)
     uint8_t *gen_scratch;                    // [N][gen_scratch_stride] generator work space
     int ep_cap;
     long long ep_buf_bins;                   // bins of the whole env (buffer stride), not of a launch slice

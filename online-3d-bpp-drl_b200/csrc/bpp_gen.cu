@@ -39,15 +39,16 @@ struct GenRng {
     }
 };
 
+constexpr int kGenLanes = 4;     // episodes generated per warp (see bpp_gen_kernel)
 constexpr int kStack = 96;      // DFS stack of the cut1 split tree: depth <= (L+W+H)/min(lo) <= 96 for L,W<=32,H<=255,lo>=... checked on the host
 
 __device__ __forceinline__ uint32_t pack_item(int x, int y, int z) { return (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)z << 16); }
 
 // cut1 into `out` (packed items), using `leaf` (cap pieces) and `lists` (2*cap uint16) as scratch.  Returns the length.
-__device__ int gen_cut1(const EnvParams &p, GenRng &g, uint32_t *out, Piece *leaf, uint16_t *lists, int cap)
+__device__ int gen_cut1(const EnvParams &p, GenRng &g, uint32_t *out, Piece *leaf, uint16_t *lists, uint8_t *shadow,
+                        Piece *stack, int cap)
 {
     const int L = p.L, W = p.W, H = p.H;
-    Piece stack[kStack];
     int sp = 0, n_leaf = 0;
     stack[sp++] = Piece{(uint8_t)L, (uint8_t)W, (uint8_t)H, 0, 0, 0};
     while (sp > 0) {
@@ -69,21 +70,33 @@ __device__ int gen_cut1(const EnvParams &p, GenRng &g, uint32_t *out, Piece *lea
         if (sp + 2 <= kStack) { stack[sp++] = p2; stack[sp++] = p1; }  // p1 first => in-order leaves
     }
     // ordering phase: generate_box_size / _add_candidate / _update, cutCreator.py:98-128
-    uint8_t shadow[kMaxSide * kMaxSide];
     for (int k = 0; k < L * W; ++k) shadow[k] = 0;
     uint16_t *meta = lists, *cand = lists + cap;
     int n_meta = n_leaf, n_cand = 0, n_out = 0;
     for (int i = 0; i < n_leaf; ++i) meta[i] = (uint16_t)i;
+    // A piece is ready when the shadow heightmap equals its lz on its whole footprint.  The shadow only changes under
+    // the piece just emitted, so after the first scan (shadow == 0: ready <=> lz == 0) a waiting piece can only
+    // become ready if it overlaps the emitted footprint and sits exactly on the new height there; everything else
+    // is skipped with six comparisons.  The scan order (and therefore the candidate order) is the reference's.
+    Piece last = Piece{0, 0, 0, 0, 0, 0};
+    bool first = true;
     for (;;) {
         int keep = 0;
         for (int m = 0; m < n_meta; ++m) {
             const Piece q = leaf[meta[m]];
-            bool ready = true;
-            for (int r = 0; r < q.x && ready; ++r)
-                for (int c = 0; c < q.y; ++c)
-                    if (shadow[(q.lx + r) * W + q.ly + c] != q.lz) { ready = false; break; }
+            bool ready;
+            if (first) {
+                ready = q.lz == 0;
+            } else {
+                ready = q.lz == last.lz + last.z && q.lx < last.lx + last.x && last.lx < q.lx + q.x &&
+                        q.ly < last.ly + last.y && last.ly < q.ly + q.y;
+                for (int r = 0; r < q.x && ready; ++r)
+                    for (int c = 0; c < q.y; ++c)
+                        if (shadow[(q.lx + r) * W + q.ly + c] != q.lz) { ready = false; break; }
+            }
             if (ready) cand[n_cand++] = meta[m]; else meta[keep++] = meta[m];
         }
+        first = false;
         n_meta = keep;
         if (n_cand == 0) break;                                       // :113-115 -> sentinel from now on
         const int idx = (int)__umulhi(g.next(), (uint32_t)n_cand);    // :116
@@ -98,6 +111,7 @@ __device__ int gen_cut1(const EnvParams &p, GenRng &g, uint32_t *out, Piece *lea
         if (n_out < cap) out[n_out++] = pack_item(ox, oy, q.z);
         for (int r = 0; r < q.x; ++r)                                 // _update, :109-110
             for (int c = 0; c < q.y; ++c) shadow[(q.lx + r) * W + q.ly + c] += q.z;
+        last = q;
     }
     return n_out;
 }
@@ -147,49 +161,74 @@ __device__ int gen_cut2(const EnvParams &p, GenRng &g, uint32_t *out, Piece *inv
 
 }  // namespace
 
-// One thread per bin.  mode 0 (init): fill the current buffer with episode e0 and the spare with e0 + 1 for every
-// bin; mode 1 (refill): bins whose flag is set get episode sc.episode + 1 into the buffer they are not playing.
-__global__ void __launch_bounds__(128) bpp_gen_kernel(const EnvParams p, const int mode, const uint32_t e0)
+// One thread per episode.  mode 0 (init): every bin gets episode e0 into buffer 0 and e0 + 1 into buffer 1;
+// mode 1 (refill): the bins on the compacted refill list (appended by the step kernel at auto-reset) get episode
+// sc.episode + 1 into the buffer they are not playing.  p is the whole env (ep_bin0 == 0).
+__global__ void __launch_bounds__(128) bpp_gen_kernel(const EnvParams p, const int mode, const uint32_t e0, const int use_smem)
 {
-    const long long bin = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (bin >= p.N) return;
-    if (mode == 1 && p.gen_flag[bin] == 0) return;
-    const BinScalars s = p.sc[bin];
-    const int cur = mode == 0 ? 0 : (int)(s.traj & 1u);
-    const size_t wstride = (size_t)p.gen_scratch_stride;              // bytes of scratch per bin
-    uint8_t *scratch = p.gen_scratch + (size_t)bin * wstride;
-    for (int which = (mode == 0 ? 0 : 1); which < 2; ++which) {
-        const int buf = mode == 0 ? which : (cur ^ 1);
-        const uint32_t episode = mode == 0 ? e0 + (uint32_t)which : s.episode + 1u;
-        GenRng g;
-        g.seed_lo = p.seed_lo; g.seed_hi = p.seed_hi; g.aux = episode; g.k = 0; g.blk_idx = 0xffffffffu;
-        g.gid = p.global_offset + (unsigned long long)bin;
-        uint32_t *out = p.ep_items + ((size_t)buf * p.ep_buf_bins + (size_t)(p.ep_bin0 + bin)) * p.ep_cap;
-        int n;
-        if (p.gen_kind == 2) {
-            Piece *leaf = reinterpret_cast<Piece *>(scratch);
-            uint16_t *lists = reinterpret_cast<uint16_t *>(scratch + (((size_t)p.ep_cap * sizeof(Piece) + 15) & ~(size_t)15));
-            n = gen_cut1(p, g, out, leaf, lists, p.ep_cap);
-        } else {
-            Piece *inv = reinterpret_cast<Piece *>(scratch);
-            Piece *val = inv + p.ep_cap + 64;
-            n = gen_cut2(p, g, out, inv, val, p.ep_cap);
+    extern __shared__ __align__(16) uint8_t gen_smem[];
+    // The per-episode work is long and serial, so throughput comes from many resident warps rather than from full
+    // ones: only kGenLanes lanes of a warp take an episode each.
+    const long long n_work = mode == 0 ? (long long)p.N : (long long)*p.gen_count;
+    const int lane = threadIdx.x & 31;
+    if (lane >= kGenLanes) return;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long wi = warp_id * kGenLanes + lane; wi < n_work; wi += n_warps * kGenLanes) {
+        const long long bin = mode == 0 ? wi : (long long)p.gen_list[wi];
+        const BinScalars s = p.sc[bin];
+        const int cur = mode == 0 ? 0 : (int)(s.traj & 1u);
+        // work space: shared memory when the launch could afford it (global-memory scratch costs a DRAM/L2 round trip
+        // per dependent access of these strictly serial algorithms), else the bin's global scratch
+        uint8_t *scratch = use_smem ? gen_smem + (size_t)((threadIdx.x >> 5) * kGenLanes + lane) * (size_t)p.gen_scratch_stride
+                                    : p.gen_scratch + (size_t)bin * (size_t)p.gen_scratch_stride;
+        for (int which = (mode == 0 ? 0 : 1); which < 2; ++which) {
+            const int buf = mode == 0 ? which : (cur ^ 1);
+            const uint32_t episode = mode == 0 ? e0 + (uint32_t)which : s.episode + 1u;
+            GenRng g;
+            g.seed_lo = p.seed_lo; g.seed_hi = p.seed_hi; g.aux = episode; g.k = 0; g.blk_idx = 0xffffffffu;
+            g.gid = p.global_offset + (unsigned long long)bin;
+            uint32_t *out = p.ep_items + ((size_t)buf * p.ep_buf_bins + (size_t)bin) * p.ep_cap;
+            int n;
+            if (p.gen_kind == 2) {
+                Piece *leaf = reinterpret_cast<Piece *>(scratch);
+                const size_t o1 = ((size_t)p.ep_cap * sizeof(Piece) + 15) & ~(size_t)15;
+                const size_t o2 = o1 + (((size_t)p.ep_cap * 4 + 15) & ~(size_t)15);
+                const size_t o3 = o2 + (size_t)p.A_pad;
+                n = gen_cut1(p, g, out, leaf, reinterpret_cast<uint16_t *>(scratch + o1), scratch + o2,
+                             reinterpret_cast<Piece *>(scratch + o3), p.ep_cap);
+            } else {
+                Piece *inv = reinterpret_cast<Piece *>(scratch);
+                Piece *val = inv + p.ep_cap + 64;
+                n = gen_cut2(p, g, out, inv, val, p.ep_cap);
+            }
+            p.ep_len2[(size_t)buf * p.ep_buf_bins + (size_t)bin] = n;
         }
-        p.ep_len2[(size_t)buf * p.ep_buf_bins + (size_t)(p.ep_bin0 + bin)] = n;
     }
-    if (mode == 1) p.gen_flag[bin] = 0;
 }
 
-cudaError_t launch_gen(const EnvParams &p, int mode, uint32_t e0, cudaStream_t st)
+cudaError_t launch_gen(const EnvParams &p, int mode, uint32_t e0, int num_sms, cudaStream_t st)
 {
-    const unsigned grid = (unsigned)(((long long)p.N + 127) / 128);
-    bpp_gen_kernel<<<grid, 128, 0, st>>>(p, mode, e0);
-    return cudaGetLastError();
+    long long want = ((long long)p.N + 4 * kGenLanes - 1) / (4 * kGenLanes);      // 4 warps per block
+    const long long cap = (long long)num_sms * 12;
+    if (mode == 1 && want > cap) want = cap;              // the list length is only known on the device
+    const size_t smem = (size_t)4 * kGenLanes * (size_t)p.gen_scratch_stride;
+    const int use_smem = smem <= 200 * 1024;
+    if (use_smem && smem > 48 * 1024) {
+        cudaError_t ea = cudaFuncSetAttribute(bpp_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ea != cudaSuccess) return ea;
+    }
+    bpp_gen_kernel<<<(unsigned)want, 128, use_smem ? smem : 0, st>>>(p, mode, e0, use_smem);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || mode == 0) return e;
+    return cudaMemsetAsync(p.gen_count, 0, sizeof(int32_t), st);     // list consumed
 }
 
 size_t gen_scratch_bytes_per_bin(int gen_kind, int cap)
 {
-    if (gen_kind == 2) return ((((size_t)cap * sizeof(Piece) + 15) & ~(size_t)15) + (size_t)cap * 4 + 15) & ~(size_t)15;
+    if (gen_kind == 2)      // leaf pieces | meta + candidate lists | shadow heightmap (<= 1024) | split stack
+        return (((size_t)cap * sizeof(Piece) + 15) & ~(size_t)15) + (((size_t)cap * 4 + 15) & ~(size_t)15) + 1024 +
+               (((size_t)kStack * sizeof(Piece) + 15) & ~(size_t)15);
     return (((size_t)(cap + 64) * 2 * sizeof(Piece)) + 15) & ~(size_t)15;
 }
 

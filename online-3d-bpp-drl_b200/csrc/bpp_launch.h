@@ -12,7 +12,7 @@ cudaError_t launch_step(const EnvParams &p, const StepIO &io, int mode, int rot,
                         size_t smem, cudaStream_t st);
 
 // bpp_gen.cu
-cudaError_t launch_gen(const EnvParams &p, int mode, uint32_t e0, cudaStream_t st);
+cudaError_t launch_gen(const EnvParams &p, int mode, uint32_t e0, int num_sms, cudaStream_t st);
 size_t gen_scratch_bytes_per_bin(int gen_kind, int cap);
 
 // bpp_mask.cu

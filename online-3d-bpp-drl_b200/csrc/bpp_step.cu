@@ -378,7 +378,6 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                 if (!fresh_reset) s.episode += 1;
                 s.cnt = 0; s.vol = 0; s.pos = 0; s.traj = traj_new; s.ep_len = len_new;
                 s.box = next_new;
-                if (p.gen_kind >= 2 && !fresh_reset) p.gen_flag[mybin] = 1;  // refill the buffer just left (bpp_gen.cu)
             } else {
                 s.box = next_ok;
             }
@@ -386,6 +385,18 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             uint4 *sp = reinterpret_cast<uint4 *>(p.sc + mybin);
             sp[0] = make_uint4(s.box, (uint32_t)s.cnt, (uint32_t)s.vol, s.episode);
             sp[1] = make_uint4(s.ctr + 1u, (uint32_t)s.pos, (uint32_t)s.ep_len, s.traj);
+        }
+        if (p.gen_kind >= 2 && !fresh_reset) {
+            // bins that moved to their spare episode go on the refill list of bpp_gen_kernel (compacted, so that
+            // the generator warps are full)
+            const bool refill = have && (mode == kModeReset || finished);
+            const unsigned rb = __ballot_sync(kFull, refill);
+            if (rb) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(p.gen_count, __popc(rb));
+                base = __shfl_sync(kFull, base, 0);
+                if (refill) p.gen_list[base + __popc(rb & ((1u << lane) - 1u))] = (int32_t)(p.ep_bin0 + mybin);
+            }
         }
     }
 
