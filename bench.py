@@ -90,7 +90,7 @@ class ClockSampler(object):
             os.close(fd)
             self.out = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.out,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.out,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -140,14 +140,17 @@ def cpu_oracle_rate(size, rot, gen, seed, budget_s, n_threads=0, bins=65536, ste
         env.step(env.sample.copy())
         n_warm += 1
     t0 = time.perf_counter()
-    env.step(env.sample.copy())
-    one = time.perf_counter() - t0
-    if steps is None:
-        steps = int(max(3, min(2000, budget_s / max(one, 1e-6))))
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    done_steps = 0
+    while True:                      # fixed step count (reference arm) or a time budget (cpu_baseline of our arm)
         env.step(env.sample.copy())
+        done_steps += 1
+        if steps is not None:
+            if done_steps >= steps:
+                break
+        elif time.perf_counter() - t0 >= budget_s and done_steps >= 3:
+            break
     dt = time.perf_counter() - t0
+    steps = done_steps
     cores = os.cpu_count() if n_threads <= 0 else n_threads
     env.close()
     return {"value": bins * steps / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
@@ -179,7 +182,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS))
@@ -256,7 +259,7 @@ def main():
     cur = (cur + args.steps) & 1
 
     # ---- end to end through the host API -------------------------------------------------------------
-    e2e_steps = args.e2e_steps or max(10, min(args.steps, 50))
+    e2e_steps = args.e2e_steps or max(10, min(args.steps, 300))
     h_act = torch.empty((N,), dtype=torch.int64).pin_memory()
     h_rew = torch.empty((N,), dtype=torch.float32).pin_memory()
     h_done = torch.empty((N,), dtype=torch.uint8).pin_memory()

@@ -7,6 +7,10 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#ifndef BPP_WINDOW_REGS
+#define BPP_WINDOW_REGS 25    // footprints up to this many cells are held in registers by the mask sweep
+#endif
+
 namespace bpp {
 
 constexpr int kWarpsPerBlock = 8;
@@ -188,19 +192,35 @@ template <int X, int Y>
 __device__ __forceinline__ void window_stats_fixed(const uint8_t *w, int W, int &m, int &cnt, int &c00, int &c10,
                                                    int &c01, int &c11)
 {
-    int h[X * Y];
+    if (X * Y <= BPP_WINDOW_REGS) {
+        int h[X * Y];
 #pragma unroll
-    for (int r = 0; r < X; ++r)
+        for (int r = 0; r < X; ++r)
 #pragma unroll
-        for (int c = 0; c < Y; ++c) h[r * Y + c] = w[r * W + c];
-    m = h[0];
+            for (int c = 0; c < Y; ++c) h[r * Y + c] = w[r * W + c];
+        m = h[0];
 #pragma unroll
-    for (int k = 1; k < X * Y; ++k) m = max(m, h[k]);
-    int below = 0;
+        for (int k = 1; k < X * Y; ++k) m = max(m, h[k]);
+        int below = 0;
 #pragma unroll
-    for (int k = 0; k < X * Y; ++k) below += min(m - h[k], 1);
-    cnt = X * Y - below;
-    c00 = h[0]; c01 = h[Y - 1]; c10 = h[(X - 1) * Y]; c11 = h[X * Y - 1];
+        for (int k = 0; k < X * Y; ++k) below += min(m - h[k], 1);
+        cnt = X * Y - below;
+        c00 = h[0]; c01 = h[Y - 1]; c10 = h[(X - 1) * Y]; c11 = h[X * Y - 1];
+    } else {
+        // large footprints: two sweeps over the cells (max, then count) instead of holding X*Y registers
+        c00 = w[0]; c01 = w[Y - 1]; c10 = w[(X - 1) * W]; c11 = w[(X - 1) * W + Y - 1];
+        m = max(max(c00, c01), max(c10, c11));
+#pragma unroll
+        for (int r = 0; r < X; ++r)
+#pragma unroll
+            for (int c = 0; c < Y; ++c) m = max(m, (int)w[r * W + c]);
+        int below = 0;
+#pragma unroll
+        for (int r = 0; r < X; ++r)
+#pragma unroll
+            for (int c = 0; c < Y; ++c) below += min(m - (int)w[r * W + c], 1);
+        cnt = X * Y - below;
+    }
 }
 
 // One thread evaluates one footprint on int32 heightmaps (batched check_box entry point): max_h or -1.
