@@ -7,6 +7,9 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#ifndef BPP_SWEEP_HOIST
+#define BPP_SWEEP_HOIST 1
+#endif
 #ifndef BPP_WINDOW_REGS
 #define BPP_WINDOW_REGS 25    // footprints up to this many cells are held in registers by the mask sweep
 #endif
@@ -255,9 +258,40 @@ __device__ __forceinline__ void window_stats_switch(const uint8_t *w, int W, int
 #undef BPP_WS_CASE
 }
 
+// Candidate-position loop of one orientation.  X, Y > 0: footprint known at compile time; 0: any size.
+template <int VARIANT, int X, int Y>
+__device__ __forceinline__ int sweep_loop(const uint8_t *tile, uint8_t *smask, int W, int x, int y, int npos, int rcp,
+                                          int dW, int thr_full, int thr_most, int thr_half, int zmax, int lane)
+{
+    int total = 0;
+#pragma unroll 1
+    for (int p0 = 0; p0 < npos; p0 += 32) {
+        const int q = p0 + lane;
+        bool ok = false;
+        if (q < npos) {
+            const int i = (int)(((uint32_t)q * (uint32_t)rcp) >> 16);
+            const int idx = i * dW + q;                  // i*W + (q - i*nj)
+            const uint8_t *w = tile + idx;
+            int m, cnt, c00, c10, c01, c11;
+            if (X > 0) {
+                window_stats_fixed<(X > 0 ? X : 1), (Y > 0 ? Y : 1)>(w, W, m, cnt, c00, c10, c01, c11);
+            } else {
+                c00 = w[0]; c10 = w[(x - 1) * W]; c01 = w[y - 1]; c11 = w[(x - 1) * W + y - 1];
+                window_stats<uint8_t>(w, W, x, y, m, cnt);
+            }
+            ok = accept<VARIANT>(m, cnt, thr_full, thr_most, thr_half, zmax, c00, c10, c01, c11);
+            smask[idx] = ok ? 1 : 0;
+        }
+        total += __popc(__ballot_sync(kFull, ok));
+    }
+    return total;
+}
+
 // Mask of one orientation: lanes sweep the (L-x+1)(W-y+1) candidate positions of the tile, write
 // smask[i*W+j] = feasible, and return the number of feasible positions (warp-uniform).
 // acktr/utils.py:54-57 / envs/bpp0/bin3D.py:85-88.  smask must be zero on entry; thr = pack_thresholds(x*y).
+// BPP_SWEEP_HOIST = 1 dispatches on the footprint once per orientation (a copy of the loop per specialised
+// footprint, sides 2..5 = the reference's item range); 0 dispatches per candidate position (one loop, smaller code).
 template <int VARIANT>
 __device__ __forceinline__ int sweep_orientation(const uint8_t *tile, uint8_t *smask, int L, int W, int H,
                                                  int x, int y, int z, uint32_t thr, int lane)
@@ -267,10 +301,24 @@ __device__ __forceinline__ int sweep_orientation(const uint8_t *tile, uint8_t *s
     const int npos = pinned((L - x + 1) * nj);
     const int rcp = pinned((int)rcp16((uint32_t)nj));
     const int dW = pinned(W - nj);
-    const int code = pinned((x <= 5 && y <= 5) ? (x - 1) * 5 + (y - 1) : -1);
     const int thr_full = pinned((int)(thr & 1023u)), thr_most = pinned((int)((thr >> 10) & 1023u)),
               thr_half = pinned((int)(thr >> 20));
     const int zmax = pinned(H - z);                      // m + z <= H  <=>  m <= H - z
+#if BPP_SWEEP_HOIST
+#define BPP_SW_CASE(X, Y) case ((X) - 2) * 4 + ((Y) - 2): \
+        return sweep_loop<VARIANT, X, Y>(tile, smask, W, x, y, npos, rcp, dW, thr_full, thr_most, thr_half, zmax, lane);
+#define BPP_SW_ROW(X) BPP_SW_CASE(X, 2) BPP_SW_CASE(X, 3) BPP_SW_CASE(X, 4) BPP_SW_CASE(X, 5)
+    if (x >= 2 && x <= 5 && y >= 2 && y <= 5) {
+        switch ((x - 2) * 4 + (y - 2)) {
+            BPP_SW_ROW(2) BPP_SW_ROW(3) BPP_SW_ROW(4) BPP_SW_ROW(5)
+        default: break;
+        }
+    }
+#undef BPP_SW_ROW
+#undef BPP_SW_CASE
+    return sweep_loop<VARIANT, 0, 0>(tile, smask, W, x, y, npos, rcp, dW, thr_full, thr_most, thr_half, zmax, lane);
+#else
+    const int code = pinned((x <= 5 && y <= 5) ? (x - 1) * 5 + (y - 1) : -1);
     int total = 0;
 #pragma unroll 1
     for (int p0 = 0; p0 < npos; p0 += 32) {
@@ -287,6 +335,7 @@ __device__ __forceinline__ int sweep_orientation(const uint8_t *tile, uint8_t *s
         total += __popc(__ballot_sync(kFull, ok));
     }
     return total;
+#endif
 }
 
 }  // namespace bpp
