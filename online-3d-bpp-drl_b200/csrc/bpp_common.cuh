@@ -10,6 +10,9 @@
 #ifndef BPP_SWEEP_HOIST
 #define BPP_SWEEP_HOIST 1
 #endif
+#ifndef BPP_SWEEP_PAIR
+#define BPP_SWEEP_PAIR 0
+#endif
 #ifndef BPP_WINDOW_REGS
 #define BPP_WINDOW_REGS 25    // footprints up to this many cells are held in registers by the mask sweep
 #endif
@@ -164,6 +167,16 @@ __device__ __forceinline__ bool accept(int m, int cnt, int thr_full, int thr_mos
     }
 }
 
+// Same with the number of corners below the window maximum already known (rule v2 only needs that).
+template <int VARIANT>
+__device__ __forceinline__ bool accept_cb(int m, int cnt, int thr_full, int thr_most, int thr_half, int zmax, int c00,
+                                          int c10, int c01, int c11, int corners_below)
+{
+    if (VARIANT == 1) return accept<1>(m, cnt, thr_full, thr_most, thr_half, zmax, c00, c10, c01, c11);
+    const int need = corners_below == 0 ? thr_half : (corners_below == 1 ? thr_most : thr_full);
+    return m <= zmax && cnt >= need;
+}
+
 template <int VARIANT>
 __device__ __forceinline__ bool accept(int m, int cnt, uint32_t thr, int z, int H, int c00, int c10, int c01, int c11)
 {
@@ -193,7 +206,7 @@ __device__ __forceinline__ void window_stats(const T *w, int W, int x, int y, in
 // counted with min(m - h, 1); the four corners come out of the same registers.
 template <int X, int Y>
 __device__ __forceinline__ void window_stats_fixed(const uint8_t *w, int W, int &m, int &cnt, int &c00, int &c10,
-                                                   int &c01, int &c11)
+                                                   int &c01, int &c11, int &corners_below)
 {
     if (X * Y <= BPP_WINDOW_REGS) {
         int h[X * Y];
@@ -204,11 +217,15 @@ __device__ __forceinline__ void window_stats_fixed(const uint8_t *w, int W, int 
         m = h[0];
 #pragma unroll
         for (int k = 1; k < X * Y; ++k) m = max(m, h[k]);
+        int t[X * Y];                    // 1 where the cell is below the window maximum
+#pragma unroll
+        for (int k = 0; k < X * Y; ++k) t[k] = min(m - h[k], 1);
         int below = 0;
 #pragma unroll
-        for (int k = 0; k < X * Y; ++k) below += min(m - h[k], 1);
+        for (int k = 0; k < X * Y; ++k) below += t[k];
         cnt = X * Y - below;
         c00 = h[0]; c01 = h[Y - 1]; c10 = h[(X - 1) * Y]; c11 = h[X * Y - 1];
+        corners_below = t[0] + t[Y - 1] + t[(X - 1) * Y] + t[X * Y - 1];   // rule v2 counts corners == window maximum
     } else {
         // large footprints: two sweeps over the cells (max, then count) instead of holding X*Y registers
         c00 = w[0]; c01 = w[Y - 1]; c10 = w[(X - 1) * W]; c11 = w[(X - 1) * W + Y - 1];
@@ -223,6 +240,7 @@ __device__ __forceinline__ void window_stats_fixed(const uint8_t *w, int W, int 
 #pragma unroll
             for (int c = 0; c < Y; ++c) below += min(m - (int)w[r * W + c], 1);
         cnt = X * Y - below;
+        corners_below = min(m - c00, 1) + min(m - c01, 1) + min(m - c10, 1) + min(m - c11, 1);
     }
 }
 
@@ -243,7 +261,7 @@ __device__ __forceinline__ int check_window(const T *w, int W, int x, int y, int
 __device__ __forceinline__ void window_stats_switch(const uint8_t *w, int W, int x, int y, int code, int &m, int &cnt,
                                                     int &c00, int &c10, int &c01, int &c11)
 {
-#define BPP_WS_CASE(X, Y) case ((X) - 1) * 5 + ((Y) - 1): window_stats_fixed<X, Y>(w, W, m, cnt, c00, c10, c01, c11); break;
+#define BPP_WS_CASE(X, Y) case ((X) - 1) * 5 + ((Y) - 1): { int cb; window_stats_fixed<X, Y>(w, W, m, cnt, c00, c10, c01, c11, cb); } break;
 #define BPP_WS_ROW(X) BPP_WS_CASE(X, 1) BPP_WS_CASE(X, 2) BPP_WS_CASE(X, 3) BPP_WS_CASE(X, 4) BPP_WS_CASE(X, 5)
     if (code >= 0) {
         switch (code) {
@@ -264,22 +282,47 @@ __device__ __forceinline__ int sweep_loop(const uint8_t *tile, uint8_t *smask, i
                                           int dW, int thr_full, int thr_most, int thr_half, int zmax, int lane)
 {
     int total = 0;
+    int p0 = 0;
+#if BPP_SWEEP_PAIR
+    // EXPERIMENT, off by default: two candidate positions per lane and iteration (two independent window evaluations
+    // in flight).  Measured on B200: the duplicated window code takes the kernel from 44 KB to 64 KB of SASS, past
+    // the instruction cache, and the step gets 2x slower (0.59 ms vs 0.26 ms per 2^19 bins).
+    if (X > 0) {
 #pragma unroll 1
-    for (int p0 = 0; p0 < npos; p0 += 32) {
+        for (; p0 + 32 < npos; p0 += 64) {
+            const int q0 = p0 + lane, q1 = q0 + 32;
+            const bool v1 = q1 < npos;
+            const int i0 = (int)(((uint32_t)q0 * (uint32_t)rcp) >> 16);
+            const int i1 = (int)(((uint32_t)q1 * (uint32_t)rcp) >> 16);
+            const int idx0 = i0 * dW + q0, idx1 = v1 ? i1 * dW + q1 : 0;
+            int m0, n0, a0, b0, c0, d0, e0, m1, n1, a1, b1, c1, d1, e1;
+            window_stats_fixed<(X > 0 ? X : 1), (Y > 0 ? Y : 1)>(tile + idx0, W, m0, n0, a0, b0, c0, d0, e0);
+            window_stats_fixed<(X > 0 ? X : 1), (Y > 0 ? Y : 1)>(tile + idx1, W, m1, n1, a1, b1, c1, d1, e1);
+            const bool ok0 = accept_cb<VARIANT>(m0, n0, thr_full, thr_most, thr_half, zmax, a0, b0, c0, d0, e0);
+            const bool ok1 = v1 && accept_cb<VARIANT>(m1, n1, thr_full, thr_most, thr_half, zmax, a1, b1, c1, d1, e1);
+            smask[idx0] = ok0 ? 1 : 0;
+            if (v1) smask[idx1] = ok1 ? 1 : 0;
+            total += __popc(__ballot_sync(kFull, ok0)) + __popc(__ballot_sync(kFull, ok1));
+        }
+    }
+#endif
+#pragma unroll 1
+    for (; p0 < npos; p0 += 32) {
         const int q = p0 + lane;
         bool ok = false;
         if (q < npos) {
             const int i = (int)(((uint32_t)q * (uint32_t)rcp) >> 16);
             const int idx = i * dW + q;                  // i*W + (q - i*nj)
             const uint8_t *w = tile + idx;
-            int m, cnt, c00, c10, c01, c11;
+            int m, cnt, c00, c10, c01, c11, cb;
             if (X > 0) {
-                window_stats_fixed<(X > 0 ? X : 1), (Y > 0 ? Y : 1)>(w, W, m, cnt, c00, c10, c01, c11);
+                window_stats_fixed<(X > 0 ? X : 1), (Y > 0 ? Y : 1)>(w, W, m, cnt, c00, c10, c01, c11, cb);
             } else {
                 c00 = w[0]; c10 = w[(x - 1) * W]; c01 = w[y - 1]; c11 = w[(x - 1) * W + y - 1];
                 window_stats<uint8_t>(w, W, x, y, m, cnt);
+                cb = min(m - c00, 1) + min(m - c10, 1) + min(m - c01, 1) + min(m - c11, 1);
             }
-            ok = accept<VARIANT>(m, cnt, thr_full, thr_most, thr_half, zmax, c00, c10, c01, c11);
+            ok = accept_cb<VARIANT>(m, cnt, thr_full, thr_most, thr_half, zmax, c00, c10, c01, c11, cb);
             smask[idx] = ok ? 1 : 0;
         }
         total += __popc(__ballot_sync(kFull, ok));

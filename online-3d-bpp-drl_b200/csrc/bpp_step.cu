@@ -414,16 +414,24 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
 template <int ROT, int VARIANT, bool VEC4, int CS, bool FAST>
 static cudaError_t launch_t(const EnvParams &p, const StepIO &io, int mode, int num_sms, size_t smem, cudaStream_t st)
 {
-    static int blocks_per_sm[64] = {0};                 // per device
+    static int blocks_per_sm[64] = {0};                 // per device, for the shared-memory size of the last launch
+    static size_t smem_seen[64] = {0}, smem_opted[64] = {0};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     dev &= 63;
-    if (blocks_per_sm[dev] == 0) {
+    if (blocks_per_sm[dev] == 0 || smem_seen[dev] != smem) {
+        if (smem > 40 * 1024 && smem > smem_opted[dev]) {   // large bins: opt in to more than the default dynamic limit
+            e = cudaFuncSetAttribute(bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            smem_opted[dev] = smem;
+        }
         int b = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST>, kThreads, smem);
         if (e != cudaSuccess) return e;
         blocks_per_sm[dev] = b > 0 ? b : 1;
+        smem_seen[dev] = smem;
     }
     const long long cap = (long long)num_sms * blocks_per_sm[dev];
     // largest power-of-two batch (<= 32 bins per warp) that still gives every resident warp a batch

@@ -421,3 +421,11 @@ def test_device_rollout_glue(env_mod):
     # with a valid-only policy episodes end only when nothing fits (all-ones fallback mask) or on the action==A quirk
     assert s["mean_length"] > 5
     env.close()
+
+
+def test_extreme_sizes(env_mod):
+    """Limits of the ABI: 32x32 bins, H = 255, items up to 32 wide, bin counts that are not multiples of 32, N = 1."""
+    big = [(32, 32, 200), (1, 1, 1), (7, 31, 40), (16, 16, 100), (5, 5, 5), (32, 1, 255)]
+    run_against_oracle(env_mod, 33, (32, 32, 255), True, 2, dict(data_type="rs", box_set=big), T=40, seed=12)
+    run_against_oracle(env_mod, 1, (10, 10, 10), False, 1, dict(data_type="rs"), T=30, seed=13)
+    run_against_oracle(env_mod, 95, (20, 20, 20), True, 1, dict(data_type="rs", box_set=[(2, 2, 2), (10, 10, 3), (20, 20, 1), (9, 4, 6)]), T=40, seed=14)
