@@ -10,6 +10,9 @@
 #ifndef BPP_SWEEP_HOIST
 #define BPP_SWEEP_HOIST 1
 #endif
+#ifndef BPP_SWEEP_CONST
+#define BPP_SWEEP_CONST 1     // per-footprint constants (candidate count, reciprocal, thresholds) in the specialised loops
+#endif
 #ifndef BPP_SWEEP_PAIR
 #define BPP_SWEEP_PAIR 0
 #endif
@@ -277,10 +280,21 @@ __device__ __forceinline__ void window_stats_switch(const uint8_t *w, int W, int
 }
 
 // Candidate-position loop of one orientation.  X, Y > 0: footprint known at compile time; 0: any size.
-template <int VARIANT, int X, int Y>
-__device__ __forceinline__ int sweep_loop(const uint8_t *tile, uint8_t *smask, int W, int x, int y, int npos, int rcp,
-                                          int dW, int thr_full, int thr_most, int thr_half, int zmax, int lane)
+template <int VARIANT, int X, int Y, int CS>
+__device__ __forceinline__ int sweep_loop(const uint8_t *tile, uint8_t *smask, int W_, int x, int y, int npos_, int rcp_,
+                                          int dW_, int thr_full_, int thr_most_, int thr_half_, int zmax, int lane)
 {
+    // With the footprint (X, Y) and the bin side (CS) known at compile time everything but the tile contents and z
+    // is a constant: candidate count, row length, the reciprocal of the position decode, the three thresholds.
+    constexpr bool kConst = X > 0 && CS > 0 && BPP_SWEEP_CONST;
+    constexpr int kNj = kConst ? CS - Y + 1 : 1;
+    const int W = CS > 0 ? CS : W_;
+    const int npos = kConst ? (CS - X + 1) * kNj : npos_;
+    const int rcp = kConst ? (65536 + kNj - 1) / kNj : rcp_;
+    const int dW = kConst ? CS - kNj : dW_;
+    const int thr_full = (X > 0 && BPP_SWEEP_CONST) ? (19 * X * Y) / 20 + 1 : thr_full_;
+    const int thr_most = (X > 0 && BPP_SWEEP_CONST) ? (17 * X * Y) / 20 + 1 : thr_most_;
+    const int thr_half = (X > 0 && BPP_SWEEP_CONST) ? (X * Y) / 2 + 1 : thr_half_;
     int total = 0;
     int p0 = 0;
 #if BPP_SWEEP_PAIR
@@ -335,21 +349,21 @@ __device__ __forceinline__ int sweep_loop(const uint8_t *tile, uint8_t *smask, i
 // acktr/utils.py:54-57 / envs/bpp0/bin3D.py:85-88.  smask must be zero on entry; thr = pack_thresholds(x*y).
 // BPP_SWEEP_HOIST = 1 dispatches on the footprint once per orientation (a copy of the loop per specialised
 // footprint, sides 2..5 = the reference's item range); 0 dispatches per candidate position (one loop, smaller code).
-template <int VARIANT>
+template <int VARIANT, int CS = 0>
 __device__ __forceinline__ int sweep_orientation(const uint8_t *tile, uint8_t *smask, int L, int W, int H,
                                                  int x, int y, int z, uint32_t thr, int lane)
 {
     if (x > L || y > W) return 0;                        // range(width - x + 1) empty, utils.py:54-55
+    const int zmax = pinned(H - z);                      // m + z <= H  <=>  m <= H - z
     const int nj = W - y + 1;
-    const int npos = pinned((L - x + 1) * nj);
-    const int rcp = pinned((int)rcp16((uint32_t)nj));
+    const int npos = BPP_SWEEP_CONST && CS > 0 && x >= 2 && x <= 5 && y >= 2 && y <= 5 ? 0 : pinned((L - x + 1) * nj);
+    const int rcp = BPP_SWEEP_CONST && CS > 0 && x >= 2 && x <= 5 && y >= 2 && y <= 5 ? 0 : pinned((int)rcp16((uint32_t)nj));
     const int dW = pinned(W - nj);
     const int thr_full = pinned((int)(thr & 1023u)), thr_most = pinned((int)((thr >> 10) & 1023u)),
               thr_half = pinned((int)(thr >> 20));
-    const int zmax = pinned(H - z);                      // m + z <= H  <=>  m <= H - z
 #if BPP_SWEEP_HOIST
 #define BPP_SW_CASE(X, Y) case ((X) - 2) * 4 + ((Y) - 2): \
-        return sweep_loop<VARIANT, X, Y>(tile, smask, W, x, y, npos, rcp, dW, thr_full, thr_most, thr_half, zmax, lane);
+        return sweep_loop<VARIANT, X, Y, CS>(tile, smask, W, x, y, npos, rcp, dW, thr_full, thr_most, thr_half, zmax, lane);
 #define BPP_SW_ROW(X) BPP_SW_CASE(X, 2) BPP_SW_CASE(X, 3) BPP_SW_CASE(X, 4) BPP_SW_CASE(X, 5)
     if (x >= 2 && x <= 5 && y >= 2 && y <= 5) {
         switch ((x - 2) * 4 + (y - 2)) {
@@ -359,7 +373,7 @@ __device__ __forceinline__ int sweep_orientation(const uint8_t *tile, uint8_t *s
     }
 #undef BPP_SW_ROW
 #undef BPP_SW_CASE
-    return sweep_loop<VARIANT, 0, 0>(tile, smask, W, x, y, npos, rcp, dW, thr_full, thr_most, thr_half, zmax, lane);
+    return sweep_loop<VARIANT, 0, 0, 0>(tile, smask, W, x, y, npos, rcp, dW, thr_full, thr_most, thr_half, zmax, lane);
 #else
     const int code = pinned((x <= 5 && y <= 5) ? (x - 1) * 5 + (y - 1) : -1);
     int total = 0;

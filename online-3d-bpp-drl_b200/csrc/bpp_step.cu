@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             if (w_mask || w_sample) {
 #pragma unroll 1
                 for (int o = 0; o < (ROT ? 2 : 1); ++o)
-                    total += sweep_orientation<VARIANT>(tile, smask + o * A, L, W, H, o ? by : bx, o ? bx : by, bz, nthr, lane);
+                    total += sweep_orientation<VARIANT, CS>(tile, smask + o * A, L, W, H, o ? by : bx, o ? bx : by, bz, nthr, lane);
                 __syncwarp();
             }
 
