@@ -126,6 +126,11 @@ class ClockSampler(object):
 def cpu_oracle_rate(size, rot, gen, seed, budget_s, n_threads=0, bins=65536, steps=None, warmup=1):
     """Times the oracle (oracle/bpp_oracle.c, OpenMP) on a bounded sample of the workload."""
     import oracle as orc
+    if n_threads <= 0:      # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core it is allowed to run on
+        try:
+            n_threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n_threads = os.cpu_count() or 1
     kw = gen_kwargs(gen)
     if "trajectories" in kw:
         tr = kw.pop("trajectories")
@@ -151,7 +156,7 @@ def cpu_oracle_rate(size, rot, gen, seed, budget_s, n_threads=0, bins=65536, ste
             break
     dt = time.perf_counter() - t0
     steps = done_steps
-    cores = os.cpu_count() if n_threads <= 0 else n_threads
+    cores = n_threads
     env.close()
     return {"value": bins * steps / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
             "sample": "%d bins x %d steps of the same config (%s), oracle/bpp_oracle.c with OpenMP over bins, %.1f s"
