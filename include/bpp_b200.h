@@ -129,6 +129,14 @@ int32_t bpp_import_state(bpp_env *env, const int32_t *plain, const int32_t *box,
 /* obs/mask of the current state without stepping (cur_observation, bin3D.py:61-66). */
 int32_t bpp_observe(bpp_env *env, float *obs, float *mask, void *stream);
 
+/* -- checkpoint / resume (the reference checkpoints only the policy, main.py:186-191; the env state here is a few
+ *    device arrays, so a rollout can be resumed bit-exactly): bpp_state_bytes() is the size of an opaque blob,
+ *    bpp_save_state / bpp_load_state copy it to / from a caller-owned DEVICE buffer on `stream`.  A blob can only be
+ *    loaded into an env created with the same configuration. */
+int64_t bpp_state_bytes(bpp_env *env);
+int32_t bpp_save_state(bpp_env *env, void *blob, void *stream);
+int32_t bpp_load_state(bpp_env *env, const void *blob, void *stream);
+
 /* -- episode metrics accumulated on the device since creation (what main.py:159-162 collects from
  *    infos): out_host[4] = {episodes, sum of counter, sum of placed volume, env-steps}.
  *    Synchronises `stream`.  Cross-rank aggregation is one NCCL all-reduce of these 4 integers. */

@@ -244,6 +244,25 @@ class BinPackingVecEnv(object):
                                               self._stream()))
         return self.obs, self.location_masks
 
+    def state_dict(self):
+        """Full env state (heightmaps, per-bin records incl. RNG counters, episode buffers, metrics) as one CUDA uint8
+        tensor; `load_state_dict` resumes a rollout bit-exactly in an env created with the same arguments."""
+        n = int(self._lib.bpp_state_bytes(self._h))
+        blob = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.bpp_save_state(self._h, self._p(blob), self._stream()))
+        return {"blob": blob, "obs": self.obs.clone(), "location_masks": self.location_masks.clone(),
+                "sample": None if self.sample_t is None else self.sample_t.clone()}
+
+    def load_state_dict(self, sd):
+        blob = sd["blob"].to(device=self.device, dtype=torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.bpp_load_state(self._h, self._p(blob), self._stream()))
+        self.obs.copy_(sd["obs"])
+        self.location_masks.copy_(sd["location_masks"])
+        if self.sample_t is not None and sd.get("sample") is not None:
+            self.sample_t.copy_(sd["sample"])
+
     def metrics(self):
         """Local episode accumulators: {'episodes','sum_counter','sum_vol','steps'} (python ints)."""
         out = (C.c_uint64 * 4)()

@@ -499,6 +499,83 @@ int32_t bpp_import_state(bpp_env *env, const int32_t *plain, const int32_t *box,
     return BPP_OK;
 }
 
+namespace {
+struct StateHeader {
+    uint32_t magic, n_bins, A_pad, gen_kind;
+    uint64_t steps, ep_bytes;
+    uint32_t was_reset, pad;
+};
+struct StatePart { void *ptr; size_t bytes; };
+// device arrays that make up the env state, in blob order
+int state_parts(bpp_env *env, StatePart *parts)
+{
+    const EnvParams &p = env->p;
+    const size_t N = (size_t)p.N;
+    int n = 0;
+    parts[n++] = {env->d_hm, N * p.A_pad};
+    parts[n++] = {env->d_sc, N * sizeof(BinScalars)};
+    parts[n++] = {env->d_metrics, 4 * sizeof(unsigned long long)};
+    if (p.gen_kind >= 2) {
+        parts[n++] = {env->d_ep_items, 2 * N * p.ep_cap * sizeof(uint32_t)};
+        parts[n++] = {env->d_ep_len2, 2 * N * sizeof(int32_t)};
+    }
+    return n;
+}
+}  // namespace
+
+int64_t bpp_state_bytes(bpp_env *env)
+{
+    if (!env) return fail(BPP_ERR_INVALID, "bpp_state_bytes: null env");
+    StatePart parts[8];
+    const int n = state_parts(env, parts);
+    size_t total = 256;                                   // header, padded
+    for (int k = 0; k < n; ++k) total += (parts[k].bytes + 255) & ~(size_t)255;
+    return (int64_t)total;
+}
+
+int32_t bpp_save_state(bpp_env *env, void *blob, void *stream)
+{
+    if (int rc = enter(env, "bpp_save_state")) return rc;
+    if (!blob) return fail(BPP_ERR_INVALID, "bpp_save_state: null blob");
+    StatePart parts[8];
+    const int n = state_parts(env, parts);
+    StateHeader h{0x42505031u, (uint32_t)env->p.N, (uint32_t)env->p.A_pad, (uint32_t)env->p.gen_kind, env->steps,
+                  (uint64_t)bpp_state_bytes(env), env->was_reset ? 1u : 0u, 0u};
+    cudaStream_t st = as_stream(stream);
+    BPP_CUDA(cudaMemcpyAsync(blob, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    BPP_CUDA(cudaStreamSynchronize(st));                  // h lives on this stack frame
+    size_t off = 256;
+    for (int k = 0; k < n; ++k) {
+        BPP_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(blob) + off, parts[k].ptr, parts[k].bytes, cudaMemcpyDeviceToDevice, st));
+        off += (parts[k].bytes + 255) & ~(size_t)255;
+    }
+    return BPP_OK;
+}
+
+int32_t bpp_load_state(bpp_env *env, const void *blob, void *stream)
+{
+    if (int rc = enter(env, "bpp_load_state")) return rc;
+    if (!blob) return fail(BPP_ERR_INVALID, "bpp_load_state: null blob");
+    cudaStream_t st = as_stream(stream);
+    StateHeader h{};
+    BPP_CUDA(cudaMemcpyAsync(&h, blob, sizeof(h), cudaMemcpyDeviceToHost, st));
+    BPP_CUDA(cudaStreamSynchronize(st));
+    if (h.magic != 0x42505031u || h.n_bins != (uint32_t)env->p.N || h.A_pad != (uint32_t)env->p.A_pad ||
+        h.gen_kind != (uint32_t)env->p.gen_kind || h.ep_bytes != (uint64_t)bpp_state_bytes(env))
+        return fail(BPP_ERR_INVALID, "bpp_load_state: blob does not match this env's configuration");
+    StatePart parts[8];
+    const int n = state_parts(env, parts);
+    size_t off = 256;
+    for (int k = 0; k < n; ++k) {
+        BPP_CUDA(cudaMemcpyAsync(parts[k].ptr, static_cast<const uint8_t *>(blob) + off, parts[k].bytes, cudaMemcpyDeviceToDevice, st));
+        off += (parts[k].bytes + 255) & ~(size_t)255;
+    }
+    if (env->p.gen_kind >= 2) BPP_CUDA(cudaMemsetAsync(env->d_gen_count, 0, sizeof(int32_t), st));
+    env->steps = h.steps;
+    env->was_reset = h.was_reset != 0;
+    return BPP_OK;
+}
+
 int32_t bpp_metrics_host(bpp_env *env, uint64_t *out_host, void *stream)
 {
     if (int rc = enter(env, "bpp_metrics_host")) return rc;

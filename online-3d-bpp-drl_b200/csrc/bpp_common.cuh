@@ -7,19 +7,6 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-#ifndef BPP_SWEEP_HOIST
-#define BPP_SWEEP_HOIST 1
-#endif
-#ifndef BPP_SWEEP_CONST
-#define BPP_SWEEP_CONST 1     // per-footprint constants (candidate count, reciprocal, thresholds) in the specialised loops
-#endif
-#ifndef BPP_SWEEP_PAIR
-#define BPP_SWEEP_PAIR 0
-#endif
-#ifndef BPP_WINDOW_REGS
-#define BPP_WINDOW_REGS 25    // footprints up to this many cells are held in registers by the mask sweep
-#endif
-
 namespace bpp {
 
 constexpr int kWarpsPerBlock = 8;
@@ -211,40 +198,23 @@ template <int X, int Y>
 __device__ __forceinline__ void window_stats_fixed(const uint8_t *w, int W, int &m, int &cnt, int &c00, int &c10,
                                                    int &c01, int &c11, int &corners_below)
 {
-    if (X * Y <= BPP_WINDOW_REGS) {
-        int h[X * Y];
+    int h[X * Y];
 #pragma unroll
-        for (int r = 0; r < X; ++r)
+    for (int r = 0; r < X; ++r)
 #pragma unroll
-            for (int c = 0; c < Y; ++c) h[r * Y + c] = w[r * W + c];
-        m = h[0];
+        for (int c = 0; c < Y; ++c) h[r * Y + c] = w[r * W + c];
+    m = h[0];
 #pragma unroll
-        for (int k = 1; k < X * Y; ++k) m = max(m, h[k]);
-        int t[X * Y];                    // 1 where the cell is below the window maximum
+    for (int k = 1; k < X * Y; ++k) m = max(m, h[k]);
+    int t[X * Y];                        // 1 where the cell is below the window maximum
 #pragma unroll
-        for (int k = 0; k < X * Y; ++k) t[k] = min(m - h[k], 1);
-        int below = 0;
+    for (int k = 0; k < X * Y; ++k) t[k] = min(m - h[k], 1);
+    int below = 0;
 #pragma unroll
-        for (int k = 0; k < X * Y; ++k) below += t[k];
-        cnt = X * Y - below;
-        c00 = h[0]; c01 = h[Y - 1]; c10 = h[(X - 1) * Y]; c11 = h[X * Y - 1];
-        corners_below = t[0] + t[Y - 1] + t[(X - 1) * Y] + t[X * Y - 1];   // rule v2 counts corners == window maximum
-    } else {
-        // large footprints: two sweeps over the cells (max, then count) instead of holding X*Y registers
-        c00 = w[0]; c01 = w[Y - 1]; c10 = w[(X - 1) * W]; c11 = w[(X - 1) * W + Y - 1];
-        m = max(max(c00, c01), max(c10, c11));
-#pragma unroll
-        for (int r = 0; r < X; ++r)
-#pragma unroll
-            for (int c = 0; c < Y; ++c) m = max(m, (int)w[r * W + c]);
-        int below = 0;
-#pragma unroll
-        for (int r = 0; r < X; ++r)
-#pragma unroll
-            for (int c = 0; c < Y; ++c) below += min(m - (int)w[r * W + c], 1);
-        cnt = X * Y - below;
-        corners_below = min(m - c00, 1) + min(m - c01, 1) + min(m - c10, 1) + min(m - c11, 1);
-    }
+    for (int k = 0; k < X * Y; ++k) below += t[k];
+    cnt = X * Y - below;
+    c00 = h[0]; c01 = h[Y - 1]; c10 = h[(X - 1) * Y]; c11 = h[X * Y - 1];
+    corners_below = t[0] + t[Y - 1] + t[(X - 1) * Y] + t[X * Y - 1];   // rule v2 counts corners == window maximum
 }
 
 // One thread evaluates one footprint on int32 heightmaps (batched check_box entry point): max_h or -1.
@@ -257,28 +227,6 @@ __device__ __forceinline__ int check_window(const T *w, int W, int x, int y, int
     return accept<VARIANT>(m, cnt, pack_thresholds(x * y), z, H, c00, c10, c01, c11) ? m : -1;
 }
 
-// Window statistics with the window code unrolled for the reference's item range (1..5 per side,
-// --item-size-range, acktr/arguments.py:30): `code` = (x-1)*5 + (y-1), or -1 for any other size.  The switch is
-// warp-uniform (one indirect branch per candidate position); only the window code is specialised so that the
-// instruction footprint stays inside the instruction cache.
-__device__ __forceinline__ void window_stats_switch(const uint8_t *w, int W, int x, int y, int code, int &m, int &cnt,
-                                                    int &c00, int &c10, int &c01, int &c11)
-{
-#define BPP_WS_CASE(X, Y) case ((X) - 1) * 5 + ((Y) - 1): { int cb; window_stats_fixed<X, Y>(w, W, m, cnt, c00, c10, c01, c11, cb); } break;
-#define BPP_WS_ROW(X) BPP_WS_CASE(X, 1) BPP_WS_CASE(X, 2) BPP_WS_CASE(X, 3) BPP_WS_CASE(X, 4) BPP_WS_CASE(X, 5)
-    if (code >= 0) {
-        switch (code) {
-            BPP_WS_ROW(1) BPP_WS_ROW(2) BPP_WS_ROW(3) BPP_WS_ROW(4) BPP_WS_ROW(5)
-        default: __builtin_unreachable();
-        }
-    } else {
-        c00 = w[0]; c10 = w[(x - 1) * W]; c01 = w[y - 1]; c11 = w[(x - 1) * W + y - 1];
-        window_stats<uint8_t>(w, W, x, y, m, cnt);
-    }
-#undef BPP_WS_ROW
-#undef BPP_WS_CASE
-}
-
 // Candidate-position loop of one orientation.  X, Y > 0: footprint known at compile time; 0: any size.
 template <int VARIANT, int X, int Y, int CS>
 __device__ __forceinline__ int sweep_loop(const uint8_t *tile, uint8_t *smask, int W_, int x, int y, int npos_, int rcp_,
@@ -286,42 +234,18 @@ __device__ __forceinline__ int sweep_loop(const uint8_t *tile, uint8_t *smask, i
 {
     // With the footprint (X, Y) and the bin side (CS) known at compile time everything but the tile contents and z
     // is a constant: candidate count, row length, the reciprocal of the position decode, the three thresholds.
-    constexpr bool kConst = X > 0 && CS > 0 && BPP_SWEEP_CONST;
+    constexpr bool kConst = X > 0 && CS > 0;
     constexpr int kNj = kConst ? CS - Y + 1 : 1;
     const int W = CS > 0 ? CS : W_;
     const int npos = kConst ? (CS - X + 1) * kNj : npos_;
     const int rcp = kConst ? (65536 + kNj - 1) / kNj : rcp_;
     const int dW = kConst ? CS - kNj : dW_;
-    const int thr_full = (X > 0 && BPP_SWEEP_CONST) ? (19 * X * Y) / 20 + 1 : thr_full_;
-    const int thr_most = (X > 0 && BPP_SWEEP_CONST) ? (17 * X * Y) / 20 + 1 : thr_most_;
-    const int thr_half = (X > 0 && BPP_SWEEP_CONST) ? (X * Y) / 2 + 1 : thr_half_;
+    const int thr_full = X > 0 ? (19 * X * Y) / 20 + 1 : thr_full_;
+    const int thr_most = X > 0 ? (17 * X * Y) / 20 + 1 : thr_most_;
+    const int thr_half = X > 0 ? (X * Y) / 2 + 1 : thr_half_;
     int total = 0;
-    int p0 = 0;
-#if BPP_SWEEP_PAIR
-    // EXPERIMENT, off by default: two candidate positions per lane and iteration (two independent window evaluations
-    // in flight).  Measured on B200: the duplicated window code takes the kernel from 44 KB to 64 KB of SASS, past
-    // the instruction cache, and the step gets 2x slower (0.59 ms vs 0.26 ms per 2^19 bins).
-    if (X > 0) {
 #pragma unroll 1
-        for (; p0 + 32 < npos; p0 += 64) {
-            const int q0 = p0 + lane, q1 = q0 + 32;
-            const bool v1 = q1 < npos;
-            const int i0 = (int)(((uint32_t)q0 * (uint32_t)rcp) >> 16);
-            const int i1 = (int)(((uint32_t)q1 * (uint32_t)rcp) >> 16);
-            const int idx0 = i0 * dW + q0, idx1 = v1 ? i1 * dW + q1 : 0;
-            int m0, n0, a0, b0, c0, d0, e0, m1, n1, a1, b1, c1, d1, e1;
-            window_stats_fixed<(X > 0 ? X : 1), (Y > 0 ? Y : 1)>(tile + idx0, W, m0, n0, a0, b0, c0, d0, e0);
-            window_stats_fixed<(X > 0 ? X : 1), (Y > 0 ? Y : 1)>(tile + idx1, W, m1, n1, a1, b1, c1, d1, e1);
-            const bool ok0 = accept_cb<VARIANT>(m0, n0, thr_full, thr_most, thr_half, zmax, a0, b0, c0, d0, e0);
-            const bool ok1 = v1 && accept_cb<VARIANT>(m1, n1, thr_full, thr_most, thr_half, zmax, a1, b1, c1, d1, e1);
-            smask[idx0] = ok0 ? 1 : 0;
-            if (v1) smask[idx1] = ok1 ? 1 : 0;
-            total += __popc(__ballot_sync(kFull, ok0)) + __popc(__ballot_sync(kFull, ok1));
-        }
-    }
-#endif
-#pragma unroll 1
-    for (; p0 < npos; p0 += 32) {
+    for (int p0 = 0; p0 < npos; p0 += 32) {
         const int q = p0 + lane;
         bool ok = false;
         if (q < npos) {
@@ -347,8 +271,10 @@ __device__ __forceinline__ int sweep_loop(const uint8_t *tile, uint8_t *smask, i
 // Mask of one orientation: lanes sweep the (L-x+1)(W-y+1) candidate positions of the tile, write
 // smask[i*W+j] = feasible, and return the number of feasible positions (warp-uniform).
 // acktr/utils.py:54-57 / envs/bpp0/bin3D.py:85-88.  smask must be zero on entry; thr = pack_thresholds(x*y).
-// BPP_SWEEP_HOIST = 1 dispatches on the footprint once per orientation (a copy of the loop per specialised
-// footprint, sides 2..5 = the reference's item range); 0 dispatches per candidate position (one loop, smaller code).
+// The dispatch on the footprint happens once per orientation: footprints with sides 2..5 (the reference's item range,
+// --item-size-range, acktr/arguments.py:30) have their own copy of the loop with the window unrolled; this is as much
+// specialised code as the instruction cache takes (profiles/README.md: 44 KB of SASS runs at 76 % issue utilisation,
+// a 64 KB variant with two positions per lane ran 2x slower).  Anything else takes the generic loop.
 template <int VARIANT, int CS = 0>
 __device__ __forceinline__ int sweep_orientation(const uint8_t *tile, uint8_t *smask, int L, int W, int H,
                                                  int x, int y, int z, uint32_t thr, int lane)
@@ -356,16 +282,16 @@ __device__ __forceinline__ int sweep_orientation(const uint8_t *tile, uint8_t *s
     if (x > L || y > W) return 0;                        // range(width - x + 1) empty, utils.py:54-55
     const int zmax = pinned(H - z);                      // m + z <= H  <=>  m <= H - z
     const int nj = W - y + 1;
-    const int npos = BPP_SWEEP_CONST && CS > 0 && x >= 2 && x <= 5 && y >= 2 && y <= 5 ? 0 : pinned((L - x + 1) * nj);
-    const int rcp = BPP_SWEEP_CONST && CS > 0 && x >= 2 && x <= 5 && y >= 2 && y <= 5 ? 0 : pinned((int)rcp16((uint32_t)nj));
+    const bool spec = x >= 2 && x <= 5 && y >= 2 && y <= 5;          // footprints with their own loop below
+    const int npos = (CS > 0 && spec) ? 0 : pinned((L - x + 1) * nj);     // (those know these values at compile time)
+    const int rcp = (CS > 0 && spec) ? 0 : pinned((int)rcp16((uint32_t)nj));
     const int dW = pinned(W - nj);
     const int thr_full = pinned((int)(thr & 1023u)), thr_most = pinned((int)((thr >> 10) & 1023u)),
               thr_half = pinned((int)(thr >> 20));
-#if BPP_SWEEP_HOIST
 #define BPP_SW_CASE(X, Y) case ((X) - 2) * 4 + ((Y) - 2): \
         return sweep_loop<VARIANT, X, Y, CS>(tile, smask, W, x, y, npos, rcp, dW, thr_full, thr_most, thr_half, zmax, lane);
 #define BPP_SW_ROW(X) BPP_SW_CASE(X, 2) BPP_SW_CASE(X, 3) BPP_SW_CASE(X, 4) BPP_SW_CASE(X, 5)
-    if (x >= 2 && x <= 5 && y >= 2 && y <= 5) {
+    if (spec) {
         switch ((x - 2) * 4 + (y - 2)) {
             BPP_SW_ROW(2) BPP_SW_ROW(3) BPP_SW_ROW(4) BPP_SW_ROW(5)
         default: break;
@@ -374,25 +300,6 @@ __device__ __forceinline__ int sweep_orientation(const uint8_t *tile, uint8_t *s
 #undef BPP_SW_ROW
 #undef BPP_SW_CASE
     return sweep_loop<VARIANT, 0, 0, 0>(tile, smask, W, x, y, npos, rcp, dW, thr_full, thr_most, thr_half, zmax, lane);
-#else
-    const int code = pinned((x <= 5 && y <= 5) ? (x - 1) * 5 + (y - 1) : -1);
-    int total = 0;
-#pragma unroll 1
-    for (int p0 = 0; p0 < npos; p0 += 32) {
-        const int q = p0 + lane;
-        bool ok = false;
-        if (q < npos) {
-            const int i = (int)(((uint32_t)q * (uint32_t)rcp) >> 16);
-            const int idx = i * dW + q;                  // i*W + (q - i*nj)
-            int m, cnt, c00, c10, c01, c11;
-            window_stats_switch(tile + idx, W, x, y, code, m, cnt, c00, c10, c01, c11);
-            ok = accept<VARIANT>(m, cnt, thr_full, thr_most, thr_half, zmax, c00, c10, c01, c11);
-            smask[idx] = ok ? 1 : 0;
-        }
-        total += __popc(__ballot_sync(kFull, ok));
-    }
-    return total;
-#endif
 }
 
 }  // namespace bpp

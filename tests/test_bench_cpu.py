@@ -1,0 +1,36 @@
+"""bench.py contract on the CPU: the reference arm prints one JSON line with the agreed keys."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_reference_arm_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3",
+                          "--warmup", "3", "--workload", "cfg1"], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert out.returncode == 0, out.stderr
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "env-steps/sec" and d["unit"] == "env-steps/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 3
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=60, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_algorithmic_bytes_match_survey():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.algorithmic_bytes((10, 10, 10), False) == 2825
+    assert bench.algorithmic_bytes((10, 10, 10), True) == 3225
+    assert bench.algorithmic_bytes((20, 20, 20), False) == 11225

@@ -429,3 +429,28 @@ def test_extreme_sizes(env_mod):
     run_against_oracle(env_mod, 33, (32, 32, 255), True, 2, dict(data_type="rs", box_set=big), T=40, seed=12)
     run_against_oracle(env_mod, 1, (10, 10, 10), False, 1, dict(data_type="rs"), T=30, seed=13)
     run_against_oracle(env_mod, 95, (20, 20, 20), True, 1, dict(data_type="rs", box_set=[(2, 2, 2), (10, 10, 3), (20, 20, 1), (9, 4, 6)]), T=40, seed=14)
+
+
+@pytest.mark.parametrize("kind", ["rs", "cut2"])
+def test_checkpoint_resume_is_bit_exact(env_mod, kind):
+    import torch
+    a = env_mod.BinPackingVecEnv(500, data_type=kind, enable_rotation=True, seed=77, want_sample=True)
+    a.reset()
+    for _ in range(15):
+        a.step_device(a.sample_t.clone())
+    sd = a.state_dict()
+    ref = []
+    for _ in range(20):
+        a.step_device(a.sample_t.clone())
+        ref.append((a.obs.clone(), a.location_masks.clone(), a.reward_t.clone(), a.done_t.clone()))
+    b = env_mod.BinPackingVecEnv(500, data_type=kind, enable_rotation=True, seed=77, want_sample=True)
+    b.load_state_dict(sd)
+    for t in range(20):
+        b.step_device(b.sample_t.clone())
+        for x, y in zip(ref[t], (b.obs, b.location_masks, b.reward_t, b.done_t)):
+            assert torch.equal(x, y), t
+    assert a.metrics() == b.metrics()
+    from b200bpp import BppError
+    c = env_mod.BinPackingVecEnv(499, data_type=kind, enable_rotation=True, seed=77)
+    with pytest.raises(BppError):
+        c.load_state_dict(sd)
