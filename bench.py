@@ -264,7 +264,7 @@ def main():
     cur = (cur + args.steps) & 1
 
     # ---- end to end through the host API -------------------------------------------------------------
-    e2e_steps = args.e2e_steps or max(10, min(args.steps, 300))
+    e2e_steps = args.e2e_steps or max(10, min(args.steps, 100))
     h_act = torch.empty((N,), dtype=torch.int64).pin_memory()
     h_rew = torch.empty((N,), dtype=torch.float32).pin_memory()
     h_done = torch.empty((N,), dtype=torch.uint8).pin_memory()
