@@ -119,6 +119,19 @@ __device__ __forceinline__ T *pinned_ptr(T *ptr)      // global pointers only (t
     return ptr;
 }
 
+// 128-bit global accesses with default caching, stated in PTX so that pointers that went through pinned_ptr() (and
+// lost their address space) still compile to LDG/STG rather than generic LD/ST.
+__device__ __forceinline__ uint4 ld_global_u4(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_global_u4(uint4 *p, uint4 v)
+{
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // floor(q / d) == (q * c_rcp16[d]) >> 16 for q < 1024, 1 <= d <= 32  (c_rcp16[d] = ceil(2^16 / d))
 __constant__ uint32_t c_rcp16[kMaxSide + 1] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115, 2048};
 __device__ __forceinline__ uint32_t rcp16(uint32_t d) { return c_rcp16[d]; }

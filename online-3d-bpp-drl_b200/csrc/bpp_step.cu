@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
         // ---- phase B: warp = bin ----------------------------------------------------------------------
         uint4 pre = zero4;        // next bin's tile words, prefetched while the current bin is processed
         const bool use_pre = nq_tile <= 32 && mode != kModeReset;
-        if (use_pre && lane < nq_tile) pre = reinterpret_cast<const uint4 *>(hm0)[lane];
+        if (use_pre && lane < nq_tile) pre = ld_global_u4(reinterpret_cast<const uint4 *>(hm0) + lane);
 #pragma unroll 1
         for (int b = 0; b < nb; ++b) {
             const uint4 r0 = rec[b * kRecQuads], r1 = rec[b * kRecQuads + 1];      // broadcast reads
@@ -193,11 +193,11 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             uint8_t *ghm = hm0 + (unsigned)b * (unsigned)A_pad;
             if (use_pre) {
                 if (lane < nq_tile) tile4[lane] = pre;
-                if (b + 1 < nb && lane < nq_tile) pre = reinterpret_cast<const uint4 *>(ghm + A_pad)[lane];
+                if (b + 1 < nb && lane < nq_tile) pre = ld_global_u4(reinterpret_cast<const uint4 *>(ghm + A_pad) + lane);
             } else {
 #pragma unroll 1
                 for (int k = lane; k < nq_tile; k += 32)
-                    tile4[k] = mode == kModeReset ? zero4 : reinterpret_cast<const uint4 *>(ghm)[k];
+                    tile4[k] = mode == kModeReset ? zero4 : ld_global_u4(reinterpret_cast<const uint4 *>(ghm) + k);
             }
 #pragma unroll 1
             for (int k = lane; k < nq_mask; k += 32) smask4[k] = zero4;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             // write back
             if (mode != kModeObserve)
 #pragma unroll 1
-                for (int k = lane; k < nq_tile; k += 32) reinterpret_cast<uint4 *>(ghm)[k] = tile4[k];
+                for (int k = lane; k < nq_tile; k += 32) st_global_u4(reinterpret_cast<uint4 *>(ghm) + k, tile4[k]);
             if (w_obs) {                                                        // cur_observation, bin3D.py:61-66
                 float *o = obs0 + (unsigned)b * (unsigned)(4 * A);
                 const float fx = (float)bx, fy = (float)by, fz = (float)bz;
