@@ -129,6 +129,13 @@ int32_t bpp_import_state(bpp_env *env, const int32_t *plain, const int32_t *box,
 /* obs/mask of the current state without stepping (cur_observation, bin3D.py:61-66). */
 int32_t bpp_observe(bpp_env *env, float *obs, float *mask, void *stream);
 
+/* -- cut1 / cut2 only: the item sequence of the episode bin `bin` is currently playing (what CuttingBoxCreator /
+ *    MDlayerBoxCreator would hand out one by one, cutCreator.py:112-128, mdCreator.py:163-166), for host-side callers
+ *    that need box_creator.preview(k).  items_host receives up to cap_items triples, *len_host the episode length.
+ *    Synchronises `stream`. */
+int32_t bpp_episode_items_host(bpp_env *env, int64_t bin, uint8_t *items_host, int32_t cap_items, int32_t *len_host,
+                               void *stream);
+
 /* -- checkpoint / resume (the reference checkpoints only the policy, main.py:186-191; the env state here is a few
  *    device arrays, so a rollout can be resumed bit-exactly): bpp_state_bytes() is the size of an opaque blob,
  *    bpp_save_state / bpp_load_state copy it to / from a caller-owned DEVICE buffer on `stream`.  A blob can only be

@@ -53,6 +53,7 @@ SYMBOLS = {
     "bpp_import_state": (_i32, [_vp] * 6),
     "bpp_observe": (_i32, [_vp, _vp, _vp, _vp]),
     "bpp_metrics_host": (_i32, [_vp, _vp, _vp]),
+    "bpp_episode_items_host": (_i32, [_vp, C.c_int64, _vp, _i32, _vp, _vp]),
     "bpp_state_bytes": (C.c_int64, [_vp]),
     "bpp_save_state": (_i32, [_vp, _vp, _vp]),
     "bpp_load_state": (_i32, [_vp, _vp, _vp]),

@@ -85,6 +85,42 @@ class LoadBoxCreator(BoxCreator):
         self.box_index += 1
 
 
+class DeviceCutBoxCreator(BoxCreator):
+    """--item-seq cut1 / cut2 for the single-env view: every reset() takes the next episode that the device generator
+    (csrc/bpp_gen.cu; CuttingBoxCreator cutCreator.py:32-128 / MDlayerBoxCreator mdCreator.py:147-166) cuts for a 1-bin
+    env; past its end the reference's sentinel follows (bin size for cut1, (10,10,10) for cut2)."""
+
+    def __init__(self, kind, container_size, box_set, enable_rotation=False, seed=0, device=None):
+        super().__init__()
+        self.kind, self.bin_size = kind, tuple(int(v) for v in container_size)
+        self._args = dict(container_size=self.bin_size, box_set=box_set, enable_rotation=enable_rotation, data_type=kind,
+                          seed=seed, device=device, host_infos=False)
+        self._env = None
+        self.box_set, self.index = [], 0
+
+    def __deepcopy__(self, memo):
+        new = copy.copy(self)
+        new._env = None                         # the copy replays its current episode; a reset would need its own stream
+        new.box_list = copy.deepcopy(self.box_list, memo)
+        new.box_set = list(self.box_set)
+        return new
+
+    def reset(self):
+        self.box_list.clear()
+        if self._env is None:
+            self._env = BinPackingVecEnv(1, **self._args)
+        self._env.reset()                       # an explicit reset moves the bin to its next episode
+        self.box_set = self._env.episode_items(0)
+        self.index = 0
+
+    def generate_box_size(self, **kwargs):
+        if self.index < len(self.box_set):
+            self.box_list.append(self.box_set[self.index])
+        else:
+            self.box_list.append(self.bin_size if self.kind == "cut1" else (10, 10, 10))
+        self.index += 1
+
+
 class Space(object):
     """Host mirror of space.py:19-181; check_box / drop_box run on the device engine."""
 
@@ -132,9 +168,11 @@ class PackingGame(object):
             assert box_set is not None
             if data_type == "rs":
                 self.box_creator = RandomBoxCreator(box_set)
+            elif data_type in ("cut1", "cut2"):
+                self.box_creator = DeviceCutBoxCreator(data_type, self.bin_size, box_set, self.can_rotate, device=device,
+                                                       seed=kwargs.get("seed", 0))
             else:
-                raise NotImplementedError("single-env %s: cut episodes are generated on the device by "
-                                          "BinPackingVecEnv(data_type=%r); inject a box_creator here" % (data_type, data_type))
+                raise ValueError("data_type must be 'rs', 'cut1' or 'cut2'")
         if test:
             self.box_creator = LoadBoxCreator(data_name)
         self.act_len = self.area * (1 + self.can_rotate)
@@ -229,3 +267,15 @@ class PackingGame(object):
         if self._engine is not None:
             self._engine.close()
             self._engine = None
+
+
+# -- gym-style registry: main.py:223-227 registers 'Bpp-v0' -> envs.bpp0:PackingGame and calls gym.make(id, **kwargs) ------
+_REGISTRY = {"Bpp-v0": PackingGame}
+
+
+def register(id, entry_point=PackingGame, **kwargs):
+    _REGISTRY[id] = entry_point
+
+
+def make(id, **kwargs):
+    return _REGISTRY[id](**kwargs)

@@ -244,6 +244,15 @@ class BinPackingVecEnv(object):
                                               self._stream()))
         return self.obs, self.location_masks
 
+    def episode_items(self, bin_index=0, cap=4096):
+        """cut1 / cut2: the item sequence of the episode `bin_index` is playing, as a list of (x, y, z)."""
+        buf = np.zeros((cap, 3), dtype=np.uint8)
+        n = C.c_int32(0)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.bpp_episode_items_host(self._h, int(bin_index), buf.ctypes.data_as(C.c_void_p), cap,
+                                                        C.byref(n), self._stream()))
+        return [tuple(int(v) for v in row) for row in buf[:min(n.value, cap)]]
+
     def state_dict(self):
         """Full env state (heightmaps, per-bin records incl. RNG counters, episode buffers, metrics) as one CUDA uint8
         tensor; `load_state_dict` resumes a rollout bit-exactly in an env created with the same arguments."""

@@ -523,6 +523,35 @@ int state_parts(bpp_env *env, StatePart *parts)
 }
 }  // namespace
 
+int32_t bpp_episode_items_host(bpp_env *env, int64_t bin, uint8_t *items_host, int32_t cap_items, int32_t *len_host,
+                               void *stream)
+{
+    if (int rc = enter(env, "bpp_episode_items_host")) return rc;
+    if (env->p.gen_kind < 2) return fail(BPP_ERR_INVALID, "bpp_episode_items_host: only for the cut1 / cut2 generators");
+    if (bin < 0 || bin >= env->p.N || !items_host || !len_host || cap_items < 0)
+        return fail(BPP_ERR_INVALID, "bpp_episode_items_host: bad arguments");
+    if (!env->was_reset) return fail(BPP_ERR_STATE, "bpp_episode_items_host: call bpp_reset first");
+    cudaStream_t st = as_stream(stream);
+    BinScalars s;
+    BPP_CUDA(cudaMemcpyAsync(&s, env->d_sc + bin, sizeof(s), cudaMemcpyDeviceToHost, st));
+    BPP_CUDA(cudaStreamSynchronize(st));
+    const int buf = (int)(s.traj & 1u);
+    const int n = s.ep_len < cap_items ? s.ep_len : cap_items;
+    std::vector<uint32_t> packed((size_t)(n > 0 ? n : 1));
+    if (n > 0) {
+        BPP_CUDA(cudaMemcpyAsync(packed.data(), env->d_ep_items + ((size_t)buf * env->p.N + (size_t)bin) * env->p.ep_cap,
+                                 (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        BPP_CUDA(cudaStreamSynchronize(st));
+    }
+    for (int k = 0; k < n; ++k) {
+        items_host[3 * k] = (uint8_t)(packed[k] & 0xff);
+        items_host[3 * k + 1] = (uint8_t)((packed[k] >> 8) & 0xff);
+        items_host[3 * k + 2] = (uint8_t)((packed[k] >> 16) & 0xff);
+    }
+    *len_host = s.ep_len;
+    return BPP_OK;
+}
+
 int64_t bpp_state_bytes(bpp_env *env)
 {
     if (!env) return fail(BPP_ERR_INVALID, "bpp_state_bytes: null env");

@@ -454,3 +454,25 @@ def test_checkpoint_resume_is_bit_exact(env_mod, kind):
     c = env_mod.BinPackingVecEnv(499, data_type=kind, enable_rotation=True, seed=77)
     with pytest.raises(BppError):
         c.load_state_dict(sd)
+
+
+def test_single_env_cut_creators_and_registry(env_mod):
+    from b200bpp import bpp0
+    for kind in ("cut1", "cut2"):
+        env = bpp0.make("Bpp-v0", container_size=(10, 10, 10), box_set=env_mod.default_item_set(), data_type=kind,
+                        enable_rotation=False, seed=9)
+        env.reset()
+        seq = list(env.box_creator.box_set)
+        assert sum(x * y * z for x, y, z in seq) == 1000 and all(2 <= v <= 5 for it in seq for v in it)
+        want = orc.gen_episode(kind, (10, 10, 10), (2, 2, 2), (5, 5, 5), 9, 0, 0)[0]
+        assert [tuple(int(v) for v in r) for r in want] == seq                 # episode 0 of global bin 0, seed 9
+        assert tuple(env.box_creator.preview(3)[2]) == seq[2]
+        # play a few feasible steps through the view
+        for _ in range(4):
+            m = env.get_possible_position().reshape(-1)
+            obs, r, d, info = env.step([int(np.flatnonzero(m)[0])])
+            if d:
+                break
+        env.box_creator.preview(len(seq) + 2)                                   # past the end: sentinel
+        assert tuple(env.box_creator.box_list[-1]) == ((10, 10, 10))
+        env.close()
