@@ -163,6 +163,35 @@ def cpu_oracle_rate(size, rot, gen, seed, budget_s, n_threads=0, bins=65536, ste
                       % (bins, steps, gen, dt)}, steps, dt
 
 
+def aux_small_config(b200bpp, _cabi, dev, seed, steps=300, warmup=20):
+    """BASELINE configs[1] (4096 bins, 10x10x10, rs) beside the headline workload: launch-latency bound."""
+    import torch
+    bins, size, rot, gen, desc = WORKLOADS["cfg1"]
+    env = b200bpp.BinPackingVecEnv(bins, size, enable_rotation=rot, seed=seed, device=dev, want_sample=True, host_infos=False)
+    lib = _cabi.lib()
+    stream = torch.cuda.current_stream(dev)
+    P = lambda t: C.c_void_p(t.data_ptr())           # noqa: E731
+    bufs = [env.sample_t, torch.zeros_like(env.sample_t)]
+    env.reset()
+
+    def step(i):
+        _cabi.check(lib.bpp_step(env._h, P(bufs[i & 1]), P(env.obs), P(env.location_masks), P(env.reward_t), P(env.done_t),
+                                 P(env.counter_t), P(env.ratio_t), P(bufs[(i + 1) & 1]), C.c_void_p(stream.cuda_stream)))
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(warmup, warmup + steps):
+        step(i)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    env.close()
+    return {"workload": desc, "ms_per_step": ms, "value": bins / (ms * 1e-3), "unit": "env-steps/s", "steps": steps,
+            "note": "one kernel launch per step; at 4096 bins the step is launch-latency bound"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -342,6 +371,8 @@ def main():
             "episodes": {"finished": met[0], "mean_items": met[1] / max(met[0], 1),
                          "mean_utilisation": met[2] / max(met[0], 1) / LWH, "done_frac_last_step": done_frac},
         }
+        if world == 1 and args.workload == "target":
+            line["aux"] = {"configs[1]": aux_small_config(b200bpp, _cabi, dev, args.seed)}
         if world == 1 and not args.no_cpu_baseline:
             base, _, _ = cpu_oracle_rate(size, rot, gen, args.seed, budget_s=12.0)
             line["cpu_baseline"] = base

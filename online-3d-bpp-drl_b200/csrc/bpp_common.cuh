@@ -9,7 +9,10 @@
 
 namespace bpp {
 
-constexpr int kWarpsPerBlock = 8;
+#ifndef BPP_WARPS_PER_BLOCK
+#define BPP_WARPS_PER_BLOCK 8
+#endif
+constexpr int kWarpsPerBlock = BPP_WARPS_PER_BLOCK;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kMaxSide = 32;          // L, W <= 32 (reciprocal-multiply position decode, smem tile)
 constexpr unsigned kFull = 0xffffffffu;

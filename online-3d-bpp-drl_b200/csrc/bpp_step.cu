@@ -83,9 +83,9 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
     const bool fresh_reset = mode == kModeReset && !io.episode_inc;
 
     if (threadIdx.x < 3) blk_metrics[threadIdx.x] = 0ull;
-    {
-        const float f = (float)threadIdx.x;
-        plane_lut[threadIdx.x] = make_float4(f, f, f, f);
+    for (int v = threadIdx.x; v < 256; v += kThreads) {
+        const float f = (float)v;
+        plane_lut[v] = make_float4(f, f, f, f);
     }
     __syncthreads();
     unsigned long long m_ep = 0, m_cnt = 0, m_vol = 0;
