@@ -454,7 +454,7 @@ void orc_reset(orc_env *e, float *obs, float *mask, int64_t *sample)
     #pragma omp parallel num_threads(nt)
     {
         int32_t *scratch = (int32_t *)malloc(sizeof(int32_t) * (size_t)A * 2);
-        #pragma omp for schedule(static)
+        #pragma omp for schedule(dynamic, 128)
         for (int32_t b = 0; b < N; ++b) {
             if (!fresh) e->episode[b] += 1;             /* LoadBoxCreator.reset: index += 1 */
             memset(e->plain + (size_t)b * A, 0, sizeof(int32_t) * (size_t)A);   /* Space(*bin_size) */
@@ -485,7 +485,7 @@ void orc_step(orc_env *e, const int64_t *actions, float *obs, float *mask, float
     #pragma omp parallel num_threads(nt) reduction(+:m_ep,m_cnt,m_vol)
     {
         int32_t *scratch = (int32_t *)malloc(sizeof(int32_t) * (size_t)A * 2);
-        #pragma omp for schedule(static)
+        #pragma omp for schedule(dynamic, 128)
         for (int32_t b = 0; b < N; ++b) {
             int32_t *plain = e->plain + (size_t)b * A;
             int32_t *box = e->box + (size_t)b * 3;
