@@ -8,7 +8,8 @@
 //       remove-while-iterating traversal), then stable-sort by the z of the bottom face.
 // The emission order does not depend on the agent, so a whole episode (10^3: ~26 items, 20^3: ~210) is produced at
 // once into the bin's spare episode buffer while the current episode is being played; the step kernel swaps buffers
-// at auto-reset.  One thread per episode (the algorithms are sequential); Philox draws come from the bin's
+// at auto-reset.  One warp per episode: the parts that are sequential in the order of the random draws run on one
+// lane (or uniformly on all), list maintenance and footprint work use the 32 lanes.  Philox draws come from the bin's
 // (domain 2, aux = episode) stream in exactly the order of the CPU oracle, so device and oracle agree bit for bit.
 #include "bpp_common.cuh"
 #include "bpp_launch.h"
@@ -17,10 +18,20 @@ namespace bpp {
 
 namespace {
 
-struct Piece {
-    uint8_t x, y, z, lx, ly, lz;
-};
+// A cuboid piece of the bin: size (x, y, z) and position (lx, ly, lz), one byte each, in one 64-bit word.
+typedef unsigned long long Piece;
+__device__ __forceinline__ Piece mk_piece(int x, int y, int z, int lx, int ly, int lz)
+{
+    return (Piece)(unsigned)(x | (y << 8) | (z << 16) | (lx << 24)) | ((Piece)(unsigned)(ly | (lz << 8)) << 32);
+}
+__device__ __forceinline__ int px(Piece q) { return (int)(q & 0xff); }
+__device__ __forceinline__ int py(Piece q) { return (int)((q >> 8) & 0xff); }
+__device__ __forceinline__ int pz(Piece q) { return (int)((q >> 16) & 0xff); }
+__device__ __forceinline__ int plx(Piece q) { return (int)((q >> 24) & 0xff); }
+__device__ __forceinline__ int ply(Piece q) { return (int)((q >> 32) & 0xff); }
+__device__ __forceinline__ int plz(Piece q) { return (int)((q >> 40) & 0xff); }
 
+// The bin's generator stream (domain 2, aux = episode); every lane of the warp keeps the same state.
 struct GenRng {
     uint32_t seed_lo, seed_hi, aux, k, blk_idx;
     unsigned long long gid;
@@ -39,148 +50,221 @@ struct GenRng {
     }
 };
 
-constexpr int kGenLanes = 4;     // episodes generated per warp (see bpp_gen_kernel)
-constexpr int kStack = 96;      // DFS stack of the cut1 split tree: depth <= (L+W+H)/min(lo) <= 96 for L,W<=32,H<=255,lo>=... checked on the host
+constexpr int kStack = 96;      // DFS stack of the cut1 split tree; bpp_create checks (L+W+H)/min(lo) <= 90
 
 __device__ __forceinline__ uint32_t pack_item(int x, int y, int z) { return (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)z << 16); }
 
-// cut1 into `out` (packed items), using `leaf` (cap pieces) and `lists` (2*cap uint16) as scratch.  Returns the length.
+// list.pop(idx) / list.remove(item at idx) on an array in (shared) memory, by the whole warp
+template <typename T>
+__device__ __forceinline__ void warp_erase(T *a, int idx, int n, int lane)
+{
+    for (int k0 = idx; k0 + 1 < n; k0 += 32) {
+        const int k = k0 + lane;
+        T v = T();
+        if (k + 1 < n) v = a[k + 1];
+        __syncwarp();
+        if (k + 1 < n) a[k] = v;
+        __syncwarp();
+    }
+}
+
+// cut1, one warp per episode.  Phase 1 (the split tree) is sequential in the order of the random draws and runs on
+// lane 0; phase 2 (support-ready ordering) uses the warp: lanes test the waiting pieces against the piece just
+// emitted, check / raise footprints of the shadow heightmap cell-parallel, and compact the lists with ballots.
+// The lists keep exactly the reference's order (scan order of meta_list, appends to candidates, pop(idx)).
 __device__ int gen_cut1(const EnvParams &p, GenRng &g, uint32_t *out, Piece *leaf, uint16_t *lists, uint8_t *shadow,
-                        Piece *stack, int cap)
+                        Piece *stack, int cap, int lane)
 {
     const int L = p.L, W = p.W, H = p.H;
-    int sp = 0, n_leaf = 0;
-    stack[sp++] = Piece{(uint8_t)L, (uint8_t)W, (uint8_t)H, 0, 0, 0};
-    while (sp > 0) {
-        const Piece b = stack[--sp];
-        const int dim[3] = {b.x, b.y, b.z};
-        int bad[3], nbad = 0;
-        for (int a = 0; a < 3; ++a)                                   // _check_box, cutCreator.py:54-58
-            if (dim[a] < p.lo[a] || dim[a] > p.hi[a]) bad[nbad++] = a;
-        if (nbad == 0) { if (n_leaf < cap) leaf[n_leaf++] = b; continue; }
-        const int df = bad[__umulhi(g.next(), (uint32_t)nbad)];          // random.choice, :68
-        const int lo = p.lo[df];
-        int span = dim[df] - 2 * lo + 1;                              // randint(lo, dim - lo), :69-76
-        if (span < 1) span = 1;
-        const int cut = lo + (int)__umulhi(g.next(), (uint32_t)span);
-        Piece p1 = b, p2 = b;                                         // MetaBox.split, :16-26
-        if (df == 0) { p1.x = (uint8_t)cut; p2.x = (uint8_t)(b.x - cut); p2.lx = (uint8_t)(b.lx + cut); }
-        else if (df == 1) { p1.y = (uint8_t)cut; p2.y = (uint8_t)(b.y - cut); p2.ly = (uint8_t)(b.ly + cut); }
-        else { p1.z = (uint8_t)cut; p2.z = (uint8_t)(b.z - cut); p2.lz = (uint8_t)(b.lz + cut); }
-        if (sp + 2 <= kStack) { stack[sp++] = p2; stack[sp++] = p1; }  // p1 first => in-order leaves
+    int n_leaf = 0;
+    if (lane == 0) {
+        int sp = 0;
+        stack[sp++] = mk_piece(L, W, H, 0, 0, 0);
+        while (sp > 0) {
+            const Piece b = stack[--sp];
+            const int dim[3] = {px(b), py(b), pz(b)};
+            int bad[3], nbad = 0;
+            for (int a = 0; a < 3; ++a)                                   // _check_box, cutCreator.py:54-58
+                if (dim[a] < p.lo[a] || dim[a] > p.hi[a]) bad[nbad++] = a;
+            if (nbad == 0) { if (n_leaf < cap) leaf[n_leaf++] = b; continue; }
+            const int df = bad[__umulhi(g.next(), (uint32_t)nbad)];          // random.choice, :68
+            const int lo = p.lo[df];
+            int span = dim[df] - 2 * lo + 1;                              // randint(lo, dim - lo), :69-76
+            if (span < 1) span = 1;
+            const int cut = lo + (int)__umulhi(g.next(), (uint32_t)span);
+            Piece p1, p2;                                                 // MetaBox.split, :16-26
+            if (df == 0) { p1 = mk_piece(cut, py(b), pz(b), plx(b), ply(b), plz(b)); p2 = mk_piece(px(b) - cut, py(b), pz(b), plx(b) + cut, ply(b), plz(b)); }
+            else if (df == 1) { p1 = mk_piece(px(b), cut, pz(b), plx(b), ply(b), plz(b)); p2 = mk_piece(px(b), py(b) - cut, pz(b), plx(b), ply(b) + cut, plz(b)); }
+            else { p1 = mk_piece(px(b), py(b), cut, plx(b), ply(b), plz(b)); p2 = mk_piece(px(b), py(b), pz(b) - cut, plx(b), ply(b), plz(b) + cut); }
+            if (sp + 2 <= kStack) { stack[sp++] = p2; stack[sp++] = p1; }  // p1 first => in-order leaves
+        }
     }
+    __syncwarp();
+    n_leaf = __shfl_sync(kFull, n_leaf, 0);
+    g.k = __shfl_sync(kFull, g.k, 0);
+    g.blk_idx = 0xffffffffu;
+
     // ordering phase: generate_box_size / _add_candidate / _update, cutCreator.py:98-128
-    for (int k = 0; k < L * W; ++k) shadow[k] = 0;
     uint16_t *meta = lists, *cand = lists + cap;
+    for (int i = lane; i < n_leaf; i += 32) meta[i] = (uint16_t)i;
+    for (int k = lane; k < L * W; k += 32) shadow[k] = 0;
+    __syncwarp();
+    const unsigned lt = (1u << lane) - 1u;
     int n_meta = n_leaf, n_cand = 0, n_out = 0;
-    for (int i = 0; i < n_leaf; ++i) meta[i] = (uint16_t)i;
-    // A piece is ready when the shadow heightmap equals its lz on its whole footprint.  The shadow only changes under
-    // the piece just emitted, so after the first scan (shadow == 0: ready <=> lz == 0) a waiting piece can only
-    // become ready if it overlaps the emitted footprint and sits exactly on the new height there; everything else
-    // is skipped with six comparisons.  The scan order (and therefore the candidate order) is the reference's.
-    Piece last = Piece{0, 0, 0, 0, 0, 0};
     bool first = true;
+    Piece last = 0;
     for (;;) {
+        // A piece is ready when the shadow heightmap equals its lz on its whole footprint.  The shadow only changes
+        // under the piece just emitted, so after the first scan (shadow == 0: ready <=> lz == 0) a waiting piece can
+        // only become ready if it overlaps the emitted footprint and sits exactly on the new height there.
         int keep = 0;
-        for (int m = 0; m < n_meta; ++m) {
-            const Piece q = leaf[meta[m]];
+        for (int m0 = 0; m0 < n_meta; m0 += 32) {
+            const int m = m0 + lane;
+            const bool valid = m < n_meta;
+            const int pid = valid ? (int)meta[m] : 0;
+            const Piece q = valid ? leaf[pid] : 0;
             bool ready;
             if (first) {
-                ready = q.lz == 0;
+                ready = valid && plz(q) == 0;
             } else {
-                ready = q.lz == last.lz + last.z && q.lx < last.lx + last.x && last.lx < q.lx + q.x &&
-                        q.ly < last.ly + last.y && last.ly < q.ly + q.y;
-                for (int r = 0; r < q.x && ready; ++r)
-                    for (int c = 0; c < q.y; ++c)
-                        if (shadow[(q.lx + r) * W + q.ly + c] != q.lz) { ready = false; break; }
+                const bool pre = valid && plz(q) == plz(last) + pz(last) && plx(q) < plx(last) + px(last) &&
+                                 plx(last) < plx(q) + px(q) && ply(q) < ply(last) + py(last) && ply(last) < ply(q) + py(q);
+                ready = false;
+                unsigned pm = __ballot_sync(kFull, pre);
+                while (pm) {                                              // footprint check, lanes over the cells
+                    const int src = __ffs(pm) - 1;
+                    pm &= pm - 1;
+                    const Piece qq = __shfl_sync(kFull, q, src);
+                    const int y = py(qq), a = px(qq) * y, base = plx(qq) * W + ply(qq), lz = plz(qq);
+                    const uint32_t rcp = rcp16((uint32_t)y);
+                    bool ok = true;
+                    for (int c = lane; c < a; c += 32) {
+                        const int r = (int)(((uint32_t)c * rcp) >> 16);
+                        if (shadow[base + r * W + (c - r * y)] != lz) ok = false;
+                    }
+                    const bool all_ok = __all_sync(kFull, ok);
+                    if (lane == src) ready = all_ok;
+                }
             }
-            if (ready) cand[n_cand++] = meta[m]; else meta[keep++] = meta[m];
+            const unsigned rb = __ballot_sync(kFull, ready), kb = __ballot_sync(kFull, valid && !ready);
+            __syncwarp();                                                 // this chunk of meta has been read by every lane
+            if (ready) cand[n_cand + __popc(rb & lt)] = (uint16_t)pid;    // candidates.append, in scan order
+            if (valid && !ready) meta[keep + __popc(kb & lt)] = (uint16_t)pid;
+            n_cand += __popc(rb);
+            keep += __popc(kb);
         }
-        first = false;
         n_meta = keep;
-        if (n_cand == 0) break;                                       // :113-115 -> sentinel from now on
-        const int idx = (int)__umulhi(g.next(), (uint32_t)n_cand);    // :116
+        first = false;
+        __syncwarp();
+        if (n_cand == 0) break;                                           // :113-115 -> sentinel from now on
+        const int idx = (int)__umulhi(g.next(), (uint32_t)n_cand);        // :116
         const Piece q = leaf[cand[idx]];
-        for (int m = idx; m + 1 < n_cand; ++m) cand[m] = cand[m + 1];  // list.pop(idx)
+        __syncwarp();
+        warp_erase(cand, idx, n_cand, lane);                              // candidates.pop(idx)
         --n_cand;
-        int ox = q.x, oy = q.y;
-        if (p.rot) {                                                  // :120-126
+        int ox = px(q), oy = py(q);
+        if (p.rot) {                                                      // :120-126
             const uint32_t coin = g.next();
-            if (coin >= 0x80000000u) { ox = q.y; oy = q.x; }
+            if (coin >= 0x80000000u) { ox = py(q); oy = px(q); }
         }
-        if (n_out < cap) out[n_out++] = pack_item(ox, oy, q.z);
-        for (int r = 0; r < q.x; ++r)                                 // _update, :109-110
-            for (int c = 0; c < q.y; ++c) shadow[(q.lx + r) * W + q.ly + c] += q.z;
+        if (n_out < cap) {
+            if (lane == 0) out[n_out] = pack_item(ox, oy, pz(q));
+            ++n_out;
+        }
+        {                                                                 // _update, :109-110
+            const int y = py(q), a = px(q) * y, base = plx(q) * W + ply(q);
+            const uint32_t rcp = rcp16((uint32_t)y);
+            for (int c = lane; c < a; c += 32) {
+                const int r = (int)(((uint32_t)c * rcp) >> 16);
+                shadow[base + r * W + (c - r * y)] += (uint8_t)pz(q);
+            }
+        }
         last = q;
+        __syncwarp();
     }
     return n_out;
 }
 
-// cut2 into `out`, using `inv` / `val` (cap + 64 pieces each) as scratch.  Returns the length.
-__device__ int gen_cut2(const EnvParams &p, GenRng &g, uint32_t *out, Piece *inv, Piece *val, int cap)
+// cut2, one warp per episode.  The split loop is sequential in the order of the random draws (every lane follows it
+// with the same state; lane 0 writes, the warp shifts the lists), the final stable sort by lz is a ballot compaction
+// per level.  `inv` / `val`: cap + 64 pieces each.
+__device__ int gen_cut2(const EnvParams &p, GenRng &g, uint32_t *out, Piece *inv, Piece *val, int cap, int lane)
 {
     const int lo = p.lo[0], hi = p.hi[0];
-    int n_inv = 0, n_val = 0;
-    inv[n_inv++] = Piece{(uint8_t)p.L, (uint8_t)p.W, (uint8_t)p.H, 0, 0, 0};
-    while (n_inv > 0) {                                               // gen_benchmark, mdCreator.py:117-135
+    int n_inv = 1, n_val = 0;
+    if (lane == 0) inv[0] = mk_piece(p.L, p.W, p.H, 0, 0, 0);
+    __syncwarp();
+    while (n_inv > 0) {                                                   // gen_benchmark, mdCreator.py:117-135
         int i = 0;
         while (i < n_inv) {
             const Piece b = inv[i];
-            const int dim[3] = {b.x, b.y, b.z};
+            const int dim[3] = {px(b), py(b), pz(b)};
             int fl[3], nf = 0;
-            for (int a = 0; a < 3; ++a) if (dim[a] > hi) fl[nf++] = a;   // benchmark_split, :60-66
-            if (nf == 0) {                                            // unreachable for validated ranges
-                for (int m = i; m + 1 < n_inv; ++m) inv[m] = inv[m + 1];
-                --n_inv; if (n_val < cap) val[n_val++] = b; ++i; continue;
+            for (int a = 0; a < 3; ++a) if (dim[a] > hi) fl[nf++] = a;       // benchmark_split, :60-66
+            if (nf == 0) {                                                // unreachable for validated ranges
+                __syncwarp();
+                warp_erase(inv, i, n_inv, lane);
+                --n_inv;
+                if (n_val < cap) { if (lane == 0) val[n_val] = b; ++n_val; }
+                __syncwarp();
+                ++i;
+                continue;
             }
-            const int ax = fl[__umulhi(g.next(), (uint32_t)nf)];        // :68
+            const int ax = fl[__umulhi(g.next(), (uint32_t)nf)];            // :68
             const int cut = 1 + (int)__umulhi(g.next(), (uint32_t)dim[ax]);   // randint(1, dim)
-            if (cut < lo || dim[ax] - cut < lo) { ++i; continue; }     // rejected, retried in the next sweep
-            Piece p1 = b, p2 = b;
-            if (ax == 0) { p1.x = (uint8_t)cut; p2.x = (uint8_t)(b.x - cut); p2.lx = (uint8_t)(b.lx + cut); }          // :70-79
-            else if (ax == 1) { p1.y = (uint8_t)cut; p2.y = (uint8_t)(b.y - cut); p2.ly = (uint8_t)(b.ly + cut); }     // :80-89
-            else { p1.z = (uint8_t)(b.z - cut); p2.z = (uint8_t)cut; p2.lz = (uint8_t)(b.lz + b.z - cut); }             // :90-99
-            for (int m = i; m + 1 < n_inv; ++m) inv[m] = inv[m + 1];  // invalid_box.remove(box)
+            if (cut < lo || dim[ax] - cut < lo) { ++i; continue; }         // rejected, retried in the next sweep
+            Piece p1, p2;
+            if (ax == 0) { p1 = mk_piece(cut, py(b), pz(b), plx(b), ply(b), plz(b)); p2 = mk_piece(px(b) - cut, py(b), pz(b), plx(b) + cut, ply(b), plz(b)); }        // :70-79
+            else if (ax == 1) { p1 = mk_piece(px(b), cut, pz(b), plx(b), ply(b), plz(b)); p2 = mk_piece(px(b), py(b) - cut, pz(b), plx(b), ply(b) + cut, plz(b)); }   // :80-89
+            else { p1 = mk_piece(px(b), py(b), pz(b) - cut, plx(b), ply(b), plz(b)); p2 = mk_piece(px(b), py(b), cut, plx(b), ply(b), plz(b) + pz(b) - cut); }        // :90-99
+            __syncwarp();
+            warp_erase(inv, i, n_inv, lane);                              // invalid_box.remove(box)
             --n_inv;
             const Piece sub[2] = {p1, p2};
-            for (int s = 0; s < 2; ++s) {                             // is_valid, :110-115
+            for (int s = 0; s < 2; ++s) {                                 // is_valid, :110-115
                 const Piece q = sub[s];
-                const bool ok = q.x >= lo && q.x <= hi && q.y >= lo && q.y <= hi && q.z >= lo && q.z <= hi;
-                if (ok) { if (n_val < cap) val[n_val++] = q; }
-                else if (n_inv < cap + 64) inv[n_inv++] = q;
+                const bool ok = px(q) >= lo && px(q) <= hi && py(q) >= lo && py(q) <= hi && pz(q) >= lo && pz(q) <= hi;
+                if (ok) { if (n_val < cap) { if (lane == 0) val[n_val] = q; ++n_val; } }
+                else if (n_inv < cap + 64) { if (lane == 0) inv[n_inv] = q; ++n_inv; }
             }
-            ++i;                                                      // the iterator skips the element that slid into slot i
+            __syncwarp();
+            ++i;                                                          // the iterator skips the element that slid into slot i
         }
     }
-    int n_out = 0;                                                    // depart_box: stable sort by low_bound, :137-138
+    const unsigned lt = (1u << lane) - 1u;
+    int n_out = 0;                                                        // depart_box: stable sort by low_bound, :137-138
     for (int level = 0; level <= p.H && n_out < cap; ++level)
-        for (int v = 0; v < n_val && n_out < cap; ++v)
-            if (val[v].lz == level) out[n_out++] = pack_item(val[v].x, val[v].y, val[v].z);
+        for (int v0 = 0; v0 < n_val; v0 += 32) {
+            const int v = v0 + lane;
+            const Piece q = v < n_val ? val[v] : 0;
+            const bool hit = v < n_val && plz(q) == level;
+            const unsigned hb = __ballot_sync(kFull, hit);
+            const int pos = n_out + __popc(hb & lt);
+            if (hit && pos < cap) out[pos] = pack_item(px(q), py(q), pz(q));
+            n_out = min(cap, n_out + __popc(hb));
+        }
     return n_out;
 }
 
 }  // namespace
 
-// One thread per episode.  mode 0 (init): every bin gets episode e0 into buffer 0 and e0 + 1 into buffer 1;
+// One warp per episode.  mode 0 (init): every bin gets episode e0 into buffer 0 and e0 + 1 into buffer 1;
 // mode 1 (refill): the bins on the compacted refill list (appended by the step kernel at auto-reset) get episode
 // sc.episode + 1 into the buffer they are not playing.  p is the whole env (ep_bin0 == 0).
 __global__ void __launch_bounds__(128) bpp_gen_kernel(const EnvParams p, const int mode, const uint32_t e0, const int use_smem)
 {
     extern __shared__ __align__(16) uint8_t gen_smem[];
-    // The per-episode work is long and serial, so throughput comes from many resident warps rather than from full
-    // ones: only kGenLanes lanes of a warp take an episode each.
     const long long n_work = mode == 0 ? (long long)p.N : (long long)*p.gen_count;
     const int lane = threadIdx.x & 31;
-    if (lane >= kGenLanes) return;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long wi = warp_id * kGenLanes + lane; wi < n_work; wi += n_warps * kGenLanes) {
+    for (long long wi = warp_id; wi < n_work; wi += n_warps) {
         const long long bin = mode == 0 ? wi : (long long)p.gen_list[wi];
         const BinScalars s = p.sc[bin];
         const int cur = mode == 0 ? 0 : (int)(s.traj & 1u);
-        // work space: shared memory when the launch could afford it (global-memory scratch costs a DRAM/L2 round trip
-        // per dependent access of these strictly serial algorithms), else the bin's global scratch
-        uint8_t *scratch = use_smem ? gen_smem + (size_t)((threadIdx.x >> 5) * kGenLanes + lane) * (size_t)p.gen_scratch_stride
+        // work space: shared memory when the launch could afford it (these are chains of dependent accesses), else the
+        // bin's global scratch
+        uint8_t *scratch = use_smem ? gen_smem + (size_t)(threadIdx.x >> 5) * (size_t)p.gen_scratch_stride
                                     : p.gen_scratch + (size_t)bin * (size_t)p.gen_scratch_stride;
         for (int which = (mode == 0 ? 0 : 1); which < 2; ++which) {
             const int buf = mode == 0 ? which : (cur ^ 1);
@@ -194,25 +278,26 @@ __global__ void __launch_bounds__(128) bpp_gen_kernel(const EnvParams p, const i
                 Piece *leaf = reinterpret_cast<Piece *>(scratch);
                 const size_t o1 = ((size_t)p.ep_cap * sizeof(Piece) + 15) & ~(size_t)15;
                 const size_t o2 = o1 + (((size_t)p.ep_cap * 4 + 15) & ~(size_t)15);
-                const size_t o3 = o2 + (size_t)p.A_pad;
+                const size_t o3 = o2 + 1024;
                 n = gen_cut1(p, g, out, leaf, reinterpret_cast<uint16_t *>(scratch + o1), scratch + o2,
-                             reinterpret_cast<Piece *>(scratch + o3), p.ep_cap);
+                             reinterpret_cast<Piece *>(scratch + o3), p.ep_cap, lane);
             } else {
                 Piece *inv = reinterpret_cast<Piece *>(scratch);
                 Piece *val = inv + p.ep_cap + 64;
-                n = gen_cut2(p, g, out, inv, val, p.ep_cap);
+                n = gen_cut2(p, g, out, inv, val, p.ep_cap, lane);
             }
-            p.ep_len2[(size_t)buf * p.ep_buf_bins + (size_t)bin] = n;
+            if (lane == 0) p.ep_len2[(size_t)buf * p.ep_buf_bins + (size_t)bin] = n;
+            __syncwarp();
         }
     }
 }
 
 cudaError_t launch_gen(const EnvParams &p, int mode, uint32_t e0, int num_sms, cudaStream_t st)
 {
-    long long want = ((long long)p.N + 4 * kGenLanes - 1) / (4 * kGenLanes);      // 4 warps per block
-    const long long cap = (long long)num_sms * 12;
+    long long want = ((long long)p.N + 3) / 4;            // 4 warps per block, one episode per warp
+    const long long cap = (long long)num_sms * 16;
     if (mode == 1 && want > cap) want = cap;              // the list length is only known on the device
-    const size_t smem = (size_t)4 * kGenLanes * (size_t)p.gen_scratch_stride;
+    const size_t smem = (size_t)4 * (size_t)p.gen_scratch_stride;
     const int use_smem = smem <= 200 * 1024;
     if (use_smem && smem > 48 * 1024) {
         cudaError_t ea = cudaFuncSetAttribute(bpp_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
