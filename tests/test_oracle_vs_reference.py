@@ -92,3 +92,35 @@ def test_rollout_against_reference_env():
         assert d == (want_h == -1)
         if d:
             obs = env.reset()
+
+
+def test_replay_matches_reference_load_box_creator(golden_dir):
+    """The REAL LoadBoxCreator (test=True, dataset/cut_2.pt; binCreator.py:42-72) against the oracle's replay generator
+    fed with the re-encoded dataset: same item at every step over several episodes (index += 1 per reset, appended
+    (10,10,10), sentinel past the end), same masks, rewards and termination."""
+    import os
+    d = np.load(os.path.join(golden_dir, "datasets.npz"))
+    with rl.quiet():
+        env = REF.PackingGame(container_size=(10, 10, 10), test=True, data_name=os.path.join(REF.path, "dataset", "cut_2.pt"))
+    o = orc.OracleEnv(1, (10, 10, 10), gen="replay", traj=d["cut_2"], traj_len=d["cut_2_len"], first_traj=1)
+    rng = np.random.default_rng(4)
+    with rl.quiet():
+        obs = env.reset()
+    o.reset()
+    episodes = 0
+    for t in range(400):
+        assert np.array_equal(obs.astype(np.float32), o.obs[0]), t
+        m = np.asarray(REF.utils.get_possible_position(obs.astype(np.float32), (10, 10, 10)), np.float32)
+        assert np.array_equal(m, o.mask[0]), t
+        a = int(rng.choice(np.flatnonzero(m))) if rng.random() < 0.9 else int(rng.integers(0, 100))
+        obs, r, done, info = env.step([a])
+        o.step([a])
+        assert bool(o.done[0]) == done and np.float32(r) == o.reward[0] and info["counter"] == o.counter[0]
+        assert abs(info["ratio"] - float(o.ratio[0])) <= 1e-6
+        if done:
+            episodes += 1
+            if episodes == 6:
+                break
+            with rl.quiet():
+                obs = env.reset()
+    assert episodes == 6
