@@ -1,17 +1,12 @@
 // bpp_step.cu -- the fused per-step kernel of the batched 3D bin-packing environment (sm_100a).
 //
-// One warp owns one bin for the duration of a step (grid-stride over bins, persistent CTAs):
-//   1. two broadcast 128-bit loads fetch the bin's 32-byte scalar record, 128-bit loads stage its
-//      L x W uint8 heightmap into a shared-memory tile;
-//   2. the action is decoded and the placement checked with the env-side rule (lanes cover the
-//      footprint, warp max / ballot reductions), the footprint is raised in the tile, reward / done /
-//      info are produced, a finished episode is reset in place and the next item is fetched
-//      (Philox draw or replay row);
-//   3. lanes sweep every candidate position of the new state (one lane per position, footprint read
-//      from the tile) to build the ground-truth mask, both orientations when rotation is enabled;
-//   4. heightmap, scalars, float32 observation and float32 mask leave with 128-bit stores.
-// HBM-bound integer work: no tensor cores.  Reference behaviour cited inline (paths relative to the
-// reference root).
+// One launch per env step.  Persistent CTAs of 8 warps; every warp takes batches of 32 bins through three phases
+// (details at the kernel): scalar work with one LANE per bin, heightmap-tile work with the whole WARP per bin
+// (128-bit staged u8 tile in shared memory, placement check with warp reductions, mask sweep with one lane per
+// candidate position and the footprint unrolled at compile time, 128-bit streaming stores of the float32 observation
+// and mask), and the per-bin results again with one lane per bin.
+// HBM-bound integer work by design (no tensor cores); in practice instruction-issue limited, see DESIGN.md section 3
+// and profiles/README.md.  Reference behaviour is cited inline (paths relative to the reference root).
 #include <cstdlib>
 
 #include "bpp_common.cuh"
@@ -46,13 +41,14 @@ __device__ __forceinline__ uint32_t episode_item(const EnvParams &p, long long b
     return p.gen_kind == 2 ? ((uint32_t)p.L | ((uint32_t)p.W << 8) | ((uint32_t)p.H << 16)) : kSentinel10;
 }
 
-// The kernel works on batches of 32 bins per warp in three phases:
-//   A  (lane = bin)   scalar work once per bin instead of once per lane: state record, action decode,
-//                     Philox draws, both candidates for the next item (placement succeeds / episode ends);
-//   B  (warp = bin)   for each of the 32 bins in turn: heightmap tile, placement check + update, mask
-//                     sweep, tile / observation / mask write-back, action sampling; the per-bin scalars
-//                     arrive by warp shuffle from the lane that owns the bin;
-//   A2 (lane = bin)   reward, done, info, new state record, coalesced stores, episode metrics.
+// The kernel works on batches of 32 bins per warp (fewer for small N) in three phases:
+//   A  (lane = bin)   scalar work once per bin instead of once per lane: state record, action decode with bounds
+//                     test, Philox draws, both candidates for the next item (placement succeeds / episode ends) and
+//                     their count thresholds; everything is staged as an 80-byte record per bin in shared memory;
+//   B  (warp = bin)   for each bin of the batch in turn: record (two broadcast 128-bit loads), heightmap tile
+//                     (prefetched one bin ahead), placement check + update, mask sweep, tile / observation / mask
+//                     write-back, action sampling;
+//   A2 (lane = bin)   reward, done, info, new state record, coalesced stores, episode metrics, generator refill list.
 //
 // Template parameters: ROT = enable_rotation, VARIANT = mask rule, VEC4 = 128-bit output stores possible,
 // CS = compile-time bin side (L == W == CS; 10 and 20 are the reference's configurations, 0 = any size read
