@@ -476,3 +476,16 @@ def test_single_env_cut_creators_and_registry(env_mod):
         env.box_creator.preview(len(seq) + 2)                                   # past the end: sentinel
         assert tuple(env.box_creator.box_list[-1]) == ((10, 10, 10))
         env.close()
+
+
+def test_config5_full_shard_every_bin_vs_oracle(env_mod, golden_dir):
+    """One whole 65 536-bin shard of BASELINE configs[4] (rank 5 of 8: rotation, cut_2 replay), every bin checked
+    against the oracle at every step -- not a subsample."""
+    d = np.load(os.path.join(golden_dir, "datasets.npz"))
+    run_against_oracle(env_mod, 65536, (10, 10, 10), True, 2, dict(trajectories=(d["cut_2"], d["cut_2_len"]), first_traj=1),
+                       T=24, seed=2024, offset=5 * 65536, global_n=524288, edge_every=6)
+
+
+def test_config4_every_bin_vs_oracle(env_mod):
+    """BASELINE configs[3] at full size (262 144 bins, 20x20x20, rs): every bin against the oracle for a few steps."""
+    run_against_oracle(env_mod, 262144, (20, 20, 20), False, 2, dict(data_type="rs"), T=6, seed=7)
