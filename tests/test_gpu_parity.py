@@ -489,3 +489,28 @@ def test_config5_full_shard_every_bin_vs_oracle(env_mod, golden_dir):
 def test_config4_every_bin_vs_oracle(env_mod):
     """BASELINE configs[3] at full size (262 144 bins, 20x20x20, rs): every bin against the oracle for a few steps."""
     run_against_oracle(env_mod, 262144, (20, 20, 20), False, 2, dict(data_type="rs"), T=6, seed=7)
+
+
+@pytest.mark.parametrize("n", [1000, 40000, 140000])
+def test_step_host_pageable_buffers(env_mod, n):
+    """bpp_step_host with ordinary (pageable) host memory takes the staged copy/compute pipeline (1, 2 or 4 slices);
+    it must give what the device entry point gives."""
+    import torch
+    from b200bpp import _cabi
+    a = env_mod.BinPackingVecEnv(n, enable_rotation=True, seed=3, want_sample=True)
+    b = env_mod.BinPackingVecEnv(n, enable_rotation=True, seed=3, want_sample=True)
+    a.reset(); b.reset()
+    lib = _cabi.lib()
+    P = lambda t: C.c_void_p(t.data_ptr())
+    N = lambda x: x.ctypes.data_as(C.c_void_p)
+    for t in range(5):
+        act = a.sample_t.cpu().numpy().copy()                 # pageable
+        rew, done = np.empty(n, np.float32), np.empty(n, np.uint8)
+        cnt, rat = np.empty(n, np.int32), np.empty(n, np.float32)
+        _cabi.check(lib.bpp_step_host(b._h, N(act), P(b.obs), P(b.location_masks), N(rew), N(done), N(cnt), N(rat),
+                                      P(b.sample_t), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        a.step_device(torch.as_tensor(act, device="cuda"))
+        assert torch.equal(a.obs, b.obs) and torch.equal(a.location_masks, b.location_masks) and torch.equal(a.sample_t, b.sample_t)
+        assert np.array_equal(t2n(a.reward_t), rew) and np.array_equal(t2n(a.done_t), done)
+        assert np.array_equal(t2n(a.counter_t), cnt) and np.array_equal(t2n(a.ratio_t), rat)
+    assert a.metrics() == b.metrics()
