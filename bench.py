@@ -38,6 +38,7 @@ import numpy as np  # noqa: E402
 WORKLOADS = {
     # name: (bins per GPU, container, rotation, generator, description)
     "target": (1 << 19, (10, 10, 10), False, "rs", "2^19 parallel 10x10x10 bins per GPU, rs generator (north_star target config)"),
+    "target_rot": (1 << 19, (10, 10, 10), True, "rs", "2^19 parallel 10x10x10 bins per GPU, rs generator, rotation enabled"),
     "cfg1": (4096, (10, 10, 10), False, "rs", "BASELINE configs[1]: 4096 bins, 10x10x10, rs"),
     "cfg2": (65536, (10, 10, 10), False, "cut2_replay", "BASELINE configs[2]: 65536 bins, 10x10x10, cut_2.pt replay"),
     "cfg3": (262144, (20, 20, 20), False, "rs", "BASELINE configs[3]: 262144 bins, 20x20x20, rs"),
