@@ -84,3 +84,31 @@ def start(env, storage):
     storage.location_masks[0].copy_(env.location_masks)
     storage.step = 0
     return storage
+
+
+def play_first_episodes(env, policy, max_steps=1000, check_every=8):
+    """Resets `env` and plays every bin's FIRST episode to its end with `policy(obs, masks) -> action [N,1]`; the batched
+    form of the reference's test loop (one `env.reset()` + `env.step([act])` until done per sequence, unified_test.py:9-28
+    with --preview 1, evaluation.py:20-41).  Bins that finish keep stepping through their auto-reset episodes (their
+    results are ignored) until all are done.  -> (counter int32 [N], ratio float32 [N]) of the first episodes, on the device.
+    """
+    N, dev = env.num_envs, env.device
+    first_done = torch.zeros(N, dtype=torch.bool, device=dev)
+    counter = torch.zeros(N, dtype=torch.int32, device=dev)
+    ratio = torch.zeros(N, dtype=torch.float32, device=dev)
+    obs = env.reset()
+    masks = env.location_masks
+    for t in range(max_steps):
+        with torch.no_grad():
+            action = policy(obs, masks)
+        obs, _, done, masks = env.step_device(action)
+        newly = done.bool() & ~first_done
+        counter = torch.where(newly, env.counter_t, counter)
+        ratio = torch.where(newly, env.ratio_t, ratio)
+        first_done |= newly
+        if (t + 1) % check_every == 0 and bool(first_done.all()):       # the only host sync of the loop
+            break
+    if not bool(first_done.all()):
+        raise RuntimeError("play_first_episodes: %d bins still running after %d steps"
+                           % (int((~first_done).sum()), max_steps))
+    return counter, ratio
