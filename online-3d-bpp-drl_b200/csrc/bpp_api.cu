@@ -10,6 +10,7 @@
 
 #include "../../include/bpp_b200.h"
 #include "bpp_launch.h"
+#include "bpp_params.h"
 
 using namespace bpp;
 
@@ -138,14 +139,7 @@ int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
     e->variant = cfg->mask_variant;
     e->num_sms = num_sms;
     EnvParams &p = e->p;
-    p.N = cfg->n_bins; p.L = cfg->L; p.W = cfg->W; p.H = cfg->H;
-    p.A = cfg->L * cfg->W; p.A_pad = (p.A + 15) & ~15;
-    p.M = p.A * (e->rot ? 2 : 1); p.M_pad = (p.M + 15) & ~15;
-    p.gen_kind = cfg->gen_kind;
-    p.seed_lo = (uint32_t)cfg->seed; p.seed_hi = (uint32_t)(cfg->seed >> 32);
-    p.global_offset = (unsigned long long)cfg->global_offset;
-    p.lwh_f = (float)(cfg->L * cfg->W * cfg->H);
-    const long long global_n = cfg->global_n > 0 ? cfg->global_n : cfg->n_bins;
+    p.gen_kind = cfg->gen_kind;      // derive_params() fills the rest once the generator arguments are validated
 
 #define BPP_CREATE_CUDA(expr)                                                                       \
     do {                                                                                            \
@@ -168,7 +162,7 @@ int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
         }
         BPP_CREATE_CUDA(cudaMalloc(&e->d_items, packed.size() * 4));
         BPP_CREATE_CUDA(cudaMemcpy(e->d_items, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
-        p.n_items = cfg->n_items; p.item_set = e->d_items;
+        p.item_set = e->d_items;
         break;
     }
     case BPP_GEN_REPLAY: {
@@ -191,10 +185,7 @@ int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
         BPP_CREATE_CUDA(cudaMemcpy(e->d_traj, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
         BPP_CREATE_CUDA(cudaMalloc(&e->d_traj_len, rows * 4));
         BPP_CREATE_CUDA(cudaMemcpy(e->d_traj_len, cfg->traj_len_host, rows * 4, cudaMemcpyHostToDevice));
-        p.n_traj = cfg->n_traj; p.traj_cap = cfg->traj_cap; p.traj = e->d_traj; p.traj_len = e->d_traj_len;
-        const long long T = cfg->n_traj;
-        p.first_mod = (uint32_t)(((cfg->first_traj % T) + T) % T);
-        p.gn_mod = (uint32_t)(global_n % T);
+        p.traj = e->d_traj; p.traj_len = e->d_traj_len;
         break;
     }
     case BPP_GEN_CUT1:
@@ -211,14 +202,9 @@ int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
             lo_min = cfg->lo[a] < lo_min ? cfg->lo[a] : lo_min;
         }
         if ((cfg->L + cfg->W + cfg->H) / lo_min > 90) { bpp_destroy(e); return fail(BPP_ERR_INVALID, "bpp_create: bin too deep for the cut generators' split stack"); }
-        for (int a = 0; a < 3; ++a) { p.lo[a] = cfg->lo[axes == 3 ? a : 0]; p.hi[a] = cfg->hi[axes == 3 ? a : 0]; }
-        p.rot = e->rot;
-        const long long cap = (long long)(cfg->L / p.lo[0]) * (cfg->W / p.lo[1]) * (cfg->H / p.lo[2]);
+        const long long cap = (long long)(cfg->L / cfg->lo[0]) * (cfg->W / cfg->lo[axes == 3 ? 1 : 0]) * (cfg->H / cfg->lo[axes == 3 ? 2 : 0]);
         if (cap < 1 || cap > 60000) { bpp_destroy(e); return fail(BPP_ERR_INVALID, "bpp_create: episode capacity out of range"); }
-        p.ep_cap = (int)cap;
-        p.ep_buf_bins = cfg->n_bins;
-        p.ep_bin0 = 0;
-        p.gen_scratch_stride = (long long)gen_scratch_bytes_per_bin(cfg->gen_kind, p.ep_cap);
+        derive_params(*cfg, p);
         const size_t Nb = (size_t)cfg->n_bins;
         BPP_CREATE_CUDA(cudaMalloc(&e->d_ep_items, 2 * Nb * p.ep_cap * sizeof(uint32_t)));
         BPP_CREATE_CUDA(cudaMalloc(&e->d_ep_len2, 2 * Nb * sizeof(int32_t)));
@@ -235,6 +221,7 @@ int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
         return fail(BPP_ERR_INVALID, "bpp_create: unknown generator kind");
     }
 
+    derive_params(*cfg, p);
     const size_t N = (size_t)p.N;
     BPP_CREATE_CUDA(cudaMalloc(&e->d_hm, N * p.A_pad));
     BPP_CREATE_CUDA(cudaMemset(e->d_hm, 0, N * p.A_pad));
@@ -254,8 +241,7 @@ int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
         BPP_CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming));
     }
     BPP_CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming));
-    // per warp: heightmap tile + mask tile + 32 staged bin records of 80 bytes
-    e->smem = (size_t)kWarpsPerBlock * (p.A_pad + p.M_pad) + (size_t)kWarpsPerBlock * 32 * 80;
+    e->smem = step_smem_bytes(p);
     *out = e;
     return BPP_OK;
 }

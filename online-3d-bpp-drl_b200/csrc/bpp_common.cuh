@@ -5,7 +5,17 @@
 #pragma once
 
 #include <cstdint>
+#ifdef BPP_SIMT_EMUL
+// tests/simt/simt_emul.h: the no-GPU test suite interprets these kernel sources lane by lane on the CPU (tests only;
+// the library itself is always built by nvcc for sm_100a and has no CPU path)
+#include "simt_emul.h"
+#define BPP_LAUNCH(kernel, grid, block, smem, stream, ...) simt::launch((unsigned)(grid), (unsigned)(block), (smem), [&] { kernel(__VA_ARGS__); })
+#define BPP_DYNAMIC_SMEM(name) uint8_t *name = simt::dyn_smem()
+#else
 #include <cuda_runtime.h>
+#define BPP_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define BPP_DYNAMIC_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+#endif
 
 namespace bpp {
 
@@ -126,13 +136,21 @@ __device__ __forceinline__ T *pinned_ptr(T *ptr)      // global pointers only (t
 // lost their address space) still compile to LDG/STG rather than generic LD/ST.
 __device__ __forceinline__ uint4 ld_global_u4(const uint4 *p)
 {
+#ifdef BPP_SIMT_EMUL
+    return *p;
+#else
     uint4 v;
     asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
+#endif
 }
 __device__ __forceinline__ void st_global_u4(uint4 *p, uint4 v)
 {
+#ifdef BPP_SIMT_EMUL
+    *p = v;
+#else
     asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#endif
 }
 
 // floor(q / d) == (q * c_rcp16[d]) >> 16 for q < 1024, 1 <= d <= 32  (c_rcp16[d] = ceil(2^16 / d))

@@ -253,7 +253,7 @@ __device__ int gen_cut2(const EnvParams &p, GenRng &g, uint32_t *out, Piece *inv
 // sc.episode + 1 into the buffer they are not playing.  p is the whole env (ep_bin0 == 0).
 __global__ void __launch_bounds__(128) bpp_gen_kernel(const EnvParams p, const int mode, const uint32_t e0, const int use_smem)
 {
-    extern __shared__ __align__(16) uint8_t gen_smem[];
+    BPP_DYNAMIC_SMEM(gen_smem);
     const long long n_work = mode == 0 ? (long long)p.N : (long long)*p.gen_count;
     const int lane = threadIdx.x & 31;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -303,7 +303,7 @@ cudaError_t launch_gen(const EnvParams &p, int mode, uint32_t e0, int num_sms, c
         cudaError_t ea = cudaFuncSetAttribute(bpp_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ea != cudaSuccess) return ea;
     }
-    bpp_gen_kernel<<<(unsigned)want, 128, use_smem ? smem : 0, st>>>(p, mode, e0, use_smem);
+    BPP_LAUNCH((bpp_gen_kernel), (unsigned)want, 128, use_smem ? smem : 0, st, p, mode, e0, use_smem);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || mode == 0) return e;
     return cudaMemsetAsync(p.gen_count, 0, sizeof(int32_t), st);     // list consumed

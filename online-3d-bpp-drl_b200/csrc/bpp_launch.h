@@ -1,9 +1,7 @@
 // bpp_launch.h -- host-side declarations shared by the translation units of libbpp_b200.
 #pragma once
 
-#include <cuda_runtime.h>
-
-#include "bpp_common.cuh"
+#include "bpp_common.cuh"      // brings in <cuda_runtime.h>
 
 namespace bpp {
 

@@ -1,6 +1,8 @@
 // bpp_mask.cu -- stateless kernels: ground-truth masks from observations / raw heightmaps, batched
 // check_box, state import/export in the reference's dtypes, Philox self-test.
-#include <curand_kernel.h>
+#ifndef BPP_SIMT_EMUL
+#include <curand_kernel.h>     // only for the stream-layout self-test at the end of this file
+#endif
 
 #include "bpp_common.cuh"
 #include "bpp_launch.h"
@@ -14,7 +16,7 @@ template <int ROT, int VARIANT, int SRC>
 __global__ void __launch_bounds__(kThreads) bpp_mask_kernel(const void *src, const int32_t *box, int n, int L, int W,
                                                             int H, int A_pad, int M_pad, float *mask)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
+    BPP_DYNAMIC_SMEM(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *tile = smem + (size_t)warp * (A_pad + M_pad);
     uint8_t *smask = tile + A_pad;
@@ -54,11 +56,11 @@ static cudaError_t launch_mask_t(const void *src, const int32_t *box, int n, int
     const int A = L * W, A_pad = (A + 15) & ~15, M = A * (rot ? 2 : 1), M_pad = (M + 15) & ~15;
     const size_t smem = (size_t)kWarpsPerBlock * (A_pad + M_pad);
     if (rot) {
-        if (variant == 1) bpp_mask_kernel<1, 1, SRC><<<grid, kThreads, smem, st>>>(src, box, n, L, W, H, A_pad, M_pad, mask);
-        else bpp_mask_kernel<1, 2, SRC><<<grid, kThreads, smem, st>>>(src, box, n, L, W, H, A_pad, M_pad, mask);
+        if (variant == 1) BPP_LAUNCH((bpp_mask_kernel<1, 1, SRC>), grid, kThreads, smem, st, src, box, n, L, W, H, A_pad, M_pad, mask);
+        else BPP_LAUNCH((bpp_mask_kernel<1, 2, SRC>), grid, kThreads, smem, st, src, box, n, L, W, H, A_pad, M_pad, mask);
     } else {
-        if (variant == 1) bpp_mask_kernel<0, 1, SRC><<<grid, kThreads, smem, st>>>(src, box, n, L, W, H, A_pad, M_pad, mask);
-        else bpp_mask_kernel<0, 2, SRC><<<grid, kThreads, smem, st>>>(src, box, n, L, W, H, A_pad, M_pad, mask);
+        if (variant == 1) BPP_LAUNCH((bpp_mask_kernel<0, 1, SRC>), grid, kThreads, smem, st, src, box, n, L, W, H, A_pad, M_pad, mask);
+        else BPP_LAUNCH((bpp_mask_kernel<0, 2, SRC>), grid, kThreads, smem, st, src, box, n, L, W, H, A_pad, M_pad, mask);
     }
     return cudaGetLastError();
 }
@@ -95,7 +97,7 @@ cudaError_t launch_check_box(const int32_t *plain, const int32_t *query, int n, 
                              int32_t *out, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
-    bpp_check_box_kernel<<<(n + 127) / 128, 128, 0, st>>>(plain, query, n, L, W, H, variant, out);
+    BPP_LAUNCH((bpp_check_box_kernel), (n + 127) / 128, 128, 0, st, plain, query, n, L, W, H, variant, out);
     return cudaGetLastError();
 }
 
@@ -141,7 +143,7 @@ cudaError_t launch_export_state(const EnvParams &p, int32_t *plain, int32_t *box
                                 cudaStream_t st)
 {
     const long long n = (long long)p.N * p.A;
-    bpp_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, plain, box, counter, vol);
+    BPP_LAUNCH((bpp_export_kernel), (unsigned)((n + 255) / 256), 256, 0, st, p, plain, box, counter, vol);
     return cudaGetLastError();
 }
 
@@ -149,7 +151,7 @@ cudaError_t launch_import_state(const EnvParams &p, const int32_t *plain, const 
                                 const int32_t *vol, cudaStream_t st)
 {
     const long long n = (long long)p.N * p.A;
-    bpp_import_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, plain, box, counter, vol);
+    BPP_LAUNCH((bpp_import_kernel), (unsigned)((n + 255) / 256), 256, 0, st, p, plain, box, counter, vol);
     return cudaGetLastError();
 }
 
@@ -164,10 +166,11 @@ cudaError_t launch_debug_draws(unsigned long long seed, uint32_t domain, uint32_
                                uint32_t *out, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
-    bpp_debug_draws_kernel<<<(n + 127) / 128, 128, 0, st>>>(seed, domain, aux, gid, n, out);
+    BPP_LAUNCH((bpp_debug_draws_kernel), (n + 127) / 128, 128, 0, st, seed, domain, aux, gid, n, out);
     return cudaGetLastError();
 }
 
+#ifndef BPP_SIMT_EMUL
 // cuRAND's own Philox4_32_10 stream, for the test that the hand-written generator above reproduces it:
 // out[i] = i-th curand() after curand_init(seed, subsequence, 0).
 __global__ void bpp_debug_curand_kernel(unsigned long long seed, unsigned long long subsequence, int n, uint32_t *out)
@@ -183,8 +186,9 @@ cudaError_t launch_debug_curand(unsigned long long seed, unsigned long long subs
                                 cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
-    bpp_debug_curand_kernel<<<1, 32, 0, st>>>(seed, subsequence, n, out);
+    BPP_LAUNCH((bpp_debug_curand_kernel), 1, 32, 0, st, seed, subsequence, n, out);
     return cudaGetLastError();
 }
+#endif
 
 }  // namespace bpp

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
 {
     const int mode = FAST ? (int)kModeStep : mode_arg;
     const bool w_obs = FAST || io.obs != nullptr, w_mask = FAST || io.mask != nullptr, w_sample = FAST || io.sample != nullptr;
-    extern __shared__ __align__(16) uint8_t smem[];
+    BPP_DYNAMIC_SMEM(smem);
     __shared__ unsigned long long blk_metrics[3];
     __shared__ float4 plane_lut[256];                 // (v, v, v, v) for the constant x / y / z planes of the observation
 
@@ -444,7 +444,7 @@ static cudaError_t launch_t(const EnvParams &p, const StepIO &io, int mode, int 
     const long long batches = ((long long)p.N + (1 << q.bpw_log2) - 1) >> q.bpw_log2;
     const long long want = (batches + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int grid = (int)(want < cap ? want : cap);
-    bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST><<<grid, kThreads, smem, st>>>(q, io, mode);
+    BPP_LAUNCH((bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST>), grid, kThreads, smem, st, q, io, mode);
     return cudaGetLastError();
 }
 

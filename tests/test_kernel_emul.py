@@ -1,0 +1,148 @@
+"""The CUDA kernel SOURCES, interpreted lane by lane on the CPU (tests/simt/), against the oracle and the reference's
+golden traces.
+
+This is not a CPU path of the product (libbpp_b200.so has none): g++ compiles csrc/*.cu against a SIMT shim so that the
+no-GPU suite exercises the real kernels -- template dispatch, 32-bin warp batches, shared-memory staging, warp
+collectives, the generators' draw order -- bit for bit before a B200 is spent on them.  The `-m gpu` tests remain the
+parity tests proper; sizes here are small because every warp collective costs 32 fiber switches.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle as orc
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt"))
+import emul   # noqa: E402
+
+
+def _okw(gen_kw):
+    return dict(gen_kw)
+
+
+def run_against_oracle(N, size, rot, variant, gen_kw, T, seed, offset=0, global_n=None, edge_every=0, num_sms=2,
+                       blocks_per_sm=1, defines=()):
+    """Same protocol as tests/test_gpu_parity.py::run_against_oracle, with the interpreted kernels in place of the GPU."""
+    e = emul.EmulEnv(N, size, rot=rot, mask_variant=variant, seed=seed, global_offset=offset, global_n=global_n,
+                     num_sms=num_sms, blocks_per_sm=blocks_per_sm, defines=defines, **gen_kw)
+    o = orc.OracleEnv(N, size, rot=rot, mask_variant=variant, seed=seed, global_offset=offset, global_n=global_n,
+                      n_threads=1, **gen_kw)
+    e.reset()
+    o.reset()
+    A = size[0] * size[1]
+    rng = np.random.default_rng(seed)
+    for t in range(T + 1):
+        assert np.array_equal(e.obs, o.obs), t
+        assert np.array_equal(e.mask, o.mask), t
+        assert np.array_equal(e.sample, o.sample), t
+        if t == T:
+            break
+        actions = o.sample.copy()
+        if edge_every and t % edge_every == 0:      # out-of-range / quirk actions (action == A, negative, past the end)
+            k = rng.integers(0, N, max(1, N // 16))
+            actions[k] = rng.choice([A, -1, A * (2 if rot else 1) + 3, 0] if rot else [A, -1, 0], size=k.shape[0])
+        e.step(actions)
+        o.step(actions)
+        assert np.array_equal(e.done, o.done), t
+        assert np.array_equal(e.counter, o.counter), t
+        assert np.array_equal(e.reward, o.reward), t
+        assert np.max(np.abs(e.ratio.astype(np.float64) - o.ratio)) <= 1e-6
+    for a, b in zip(e.get_state(), o.get_state()):
+        assert np.array_equal(a, b)
+    assert e.metrics_dict() == o.metrics()
+    return e.metrics_dict()
+
+
+@pytest.mark.parametrize("rot,variant", [(False, 2), (True, 2), (True, 1)])
+def test_step_kernel_rs_10cube(rot, variant):
+    # the compile-time 10x10 fast path (CS = 10, FAST), 32-bin warp batches with a ragged tail, several batches per warp
+    m = run_against_oracle(300, (10, 10, 10), rot, variant, dict(gen="rs"), T=24, seed=1234, edge_every=7, offset=77,
+                           global_n=4096)
+    assert m["episodes"] > 300
+
+
+def test_step_kernel_20cube_and_small_batches():
+    # CS = 20; few bins on "many SMs" -> the batch-size rule picks fewer bins per warp
+    run_against_oracle(40, (20, 20, 20), False, 2, dict(gen="rs"), T=40, seed=99, num_sms=8, blocks_per_sm=2)
+
+
+def test_step_kernel_generic_sizes():
+    # CS = 0: scalar stores (L*W % 4 != 0), non-square bin, items larger than the bin, footprints outside 2..5
+    items = np.array([(x, y, z) for x in (1, 3, 8) for y in (2, 7) for z in (1, 4)], dtype=np.uint8)
+    run_against_oracle(70, (7, 9, 6), True, 1, dict(gen="rs", item_set=items), T=30, seed=3, edge_every=4)
+    run_against_oracle(33, (8, 12, 9), False, 2, dict(gen="rs"), T=30, seed=4)      # vec4 generic path
+
+
+def test_step_kernel_replay_rotation(golden_dir):
+    d = np.load(os.path.join(golden_dir, "datasets.npz"))
+    run_against_oracle(96, (10, 10, 10), True, 2, dict(gen="replay", traj=d["cut_2"], traj_len=d["cut_2_len"], first_traj=1),
+                       T=40, seed=8, offset=3 * 65536, global_n=524288, edge_every=5)
+
+
+@pytest.mark.parametrize("kind,rot", [("cut1", True), ("cut2", False)])
+def test_cut_generators(kind, rot):
+    # bpp_gen.cu: episodes cut by one warp each, Philox draws in the oracle's order; refill list from the step kernel
+    run_against_oracle(40, (10, 10, 10), rot, 2, dict(gen=kind), T=30, seed=31, offset=5000, global_n=100000, edge_every=9)
+
+
+def test_golden_rollout_through_the_interpreted_kernel(golden_dir):
+    """The reference's own trace (recorded from the Python reference) replayed through the kernel source."""
+    g = np.load(os.path.join(golden_dir, "ref_rollouts_10_rot.npz"))
+    size, rot = tuple(int(v) for v in g["size"]), bool(g["rot"])
+    T, N = g["action"].shape
+    T = min(T, 40)
+    A = size[0] * size[1]
+    for variant in (1, 2):
+        e = emul.EmulEnv(N, size, rot=rot, mask_variant=variant, gen="replay", traj=g["traj"], traj_len=g["traj_len"],
+                         first_traj=0)
+        want = g["mask_v1"] if variant == 1 else g["mask_v2"]
+        e.reset()
+        for t in range(T):
+            assert np.array_equal(e.obs[:, :A], g["hm"][t].astype(np.float32)), t
+            assert np.array_equal(e.mask, want[t].astype(np.float32)), t
+            e.step(g["action"][t])
+            assert np.array_equal(e.done, g["done"][t]) and np.array_equal(e.counter, g["counter"][t])
+            assert np.array_equal(e.reward, g["reward"][t].astype(np.float32))
+            assert np.max(np.abs(e.ratio.astype(np.float64) - g["ratio"][t])) <= 1e-6
+
+
+def test_partial_outputs_and_observe():
+    """Null output pointers (the non-FAST instantiation) and bpp_observe leave the state and the other outputs intact."""
+    e = emul.EmulEnv(64, (10, 10, 10), seed=5)
+    o = orc.OracleEnv(64, (10, 10, 10), seed=5)
+    e.reset(); o.reset()
+    for t in range(6):
+        a = o.sample.copy()
+        e.step(a, want_obs=(t % 2 == 0), want_mask=(t % 3 != 0), want_sample=True, scalars=(t % 2 == 1))
+        o.step(a)
+        assert np.array_equal(e.sample, o.sample)
+    e.observe()
+    assert np.array_equal(e.obs, o.obs) and np.array_equal(e.mask, o.mask)
+
+
+@pytest.mark.parametrize("size", [(10, 10, 10), (8, 12, 9)])
+def test_stateless_kernels_fuzz(size):
+    """bpp_mask_kernel / bpp_check_box_kernel on blocky random heightmaps, both rules, incl. the v1 != v2 region."""
+    rng = np.random.default_rng(11)
+    L, W, H = size
+    n = 48
+    plain = np.zeros((n, L, W), dtype=np.int32)
+    for b in range(n):
+        for _ in range(rng.integers(0, 8)):
+            x, y = rng.integers(1, L + 1), rng.integers(1, W + 1)
+            i, j = rng.integers(0, L - x + 1), rng.integers(0, W - y + 1)
+            plain[b, i:i + x, j:j + y] = plain[b, i:i + x, j:j + y].max() + rng.integers(1, 4)
+    plain = np.minimum(plain, H).reshape(n, -1)
+    box = np.stack([rng.integers(1, L + 1, n), rng.integers(1, W + 1, n), rng.integers(1, 5, n)], 1).astype(np.int32)
+    for rot in (False, True):
+        for variant in (1, 2):
+            want = np.stack([orc.mask(plain[b], box[b], size, rot, variant) for b in range(n)]).astype(np.float32)
+            assert np.array_equal(emul.mask_from_plain(plain, box, size, rot, variant), want)
+            obs = np.concatenate([plain] + [np.repeat(box[:, c:c + 1], L * W, 1) for c in range(3)], 1).astype(np.float32)
+            assert np.array_equal(emul.mask_from_obs(obs, size, rot, variant), want)
+    q = np.stack([box[:, 0], box[:, 1], rng.integers(-1, L, n), rng.integers(-1, W, n), box[:, 2]], 1).astype(np.int32)
+    for variant in (1, 2):
+        want = np.array([orc.check_box(plain[b], q[b, 0], q[b, 1], q[b, 2], q[b, 3], q[b, 4], size, variant) for b in range(n)])
+        assert np.array_equal(emul.check_box(plain, q, size, variant), want)
