@@ -223,8 +223,8 @@ int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
 
     derive_params(*cfg, p);
     const size_t N = (size_t)p.N;
-    BPP_CREATE_CUDA(cudaMalloc(&e->d_hm, N * p.A_pad));
-    BPP_CREATE_CUDA(cudaMemset(e->d_hm, 0, N * p.A_pad));
+    BPP_CREATE_CUDA(cudaMalloc(&e->d_hm, N * p.A_pad + kHmSlack));
+    BPP_CREATE_CUDA(cudaMemset(e->d_hm, 0, N * p.A_pad + kHmSlack));
     BPP_CREATE_CUDA(cudaMalloc(&e->d_sc, N * sizeof(BinScalars)));
     BPP_CREATE_CUDA(cudaMemset(e->d_sc, 0, N * sizeof(BinScalars)));
     BPP_CREATE_CUDA(cudaMalloc(&e->d_metrics, 4 * sizeof(unsigned long long)));

@@ -27,6 +27,22 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kMaxSide = 32;          // L, W <= 32 (reciprocal-multiply position decode, smem tile)
 constexpr unsigned kFull = 0xffffffffu;
 
+// Build variant: the mask sweep of the compile-time bin sizes evaluates TWO candidate positions per lane with the
+// 16-bit-pair integer instructions (VIMNMX3.U16x2, VIADDMNMX.U16x2); see sweep_loop_packed below.
+#ifndef BPP_PACKED_SWEEP
+#define BPP_PACKED_SWEEP 0
+#endif
+constexpr bool kPackedSweep = BPP_PACKED_SWEEP != 0;
+// Build variant: the placement check of step() (Space.check_box at the chosen position) runs in the lane-per-bin phase
+// straight from the heightmap in global memory for footprints of up to 32 cells; the warp-per-bin phase then only
+// raises the footprint.  Larger footprints (the (10,10,10) sentinels) keep the warp-cooperative check.
+#ifndef BPP_LANE_CHECK
+#define BPP_LANE_CHECK 0
+#endif
+constexpr bool kLaneCheck = BPP_LANE_CHECK != 0;
+// bytes of the per-warp "pairs" array that the packed sweep reads (one 32-bit word per heightmap cell)
+__host__ __device__ constexpr int pair_bytes(int cs) { return kPackedSweep && cs > 0 ? 4 * ((cs * cs + 15) & ~15) : 0; }
+
 // Per-bin scalar state: 32 bytes = one DRAM sector, read with two broadcast 128-bit loads.
 struct __align__(16) BinScalars {
     uint32_t box;       // x | y << 8 | z << 16  (the waiting item)
@@ -226,6 +242,35 @@ __device__ __forceinline__ void window_stats(const T *w, int W, int x, int y, in
     }
 }
 
+// Same for rows of at most 5 cells, with the row unrolled: lanes of a warp that hold different footprints stay
+// converged (the row loop runs to the warp's largest x), which is what the lane-per-bin placement check needs.
+// Always reads 5 cells per row -- up to 4 bytes past the footprint's last cell, hence kHmSlack -- and masks the ones
+// outside the footprint to -1.  Per row: maximum, cells equal to it, then the merge into the running (maximum, count).
+constexpr int kHmSlack = 16;          // readable bytes that must follow the last heightmap row of an env
+template <typename T>
+__device__ __forceinline__ void window_stats_rows5(const T *w, int W, int x, int y, int &m, int &cnt)
+{
+    m = -1;
+    cnt = 0;
+#pragma unroll 1
+    for (int r = 0; r < x; ++r) {
+        const T *row = w + r * W;
+        int h[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const int v = (int)row[c];
+            h[c] = c < y ? v : -1;
+        }
+        const int rm = max(max(max(h[0], h[1]), max(h[2], h[3])), h[4]);
+        int below = 0;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) below += min(rm - h[c], 1);
+        const int rc = 5 - below;
+        cnt = rm > m ? rc : cnt + (rm == m ? rc : 0);
+        m = max(m, rm);
+    }
+}
+
 // Same for a compile-time footprint: all cells go to registers, max tree, then the cells below the max are
 // counted with min(m - h, 1); the four corners come out of the same registers.
 template <int X, int Y>
@@ -302,6 +347,91 @@ __device__ __forceinline__ int sweep_loop(const uint8_t *tile, uint8_t *smask, i
     return total;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Packed sweep (rule v2, compile-time footprint and bin side): one lane evaluates the two horizontally adjacent
+// candidate positions (i, j) and (i, j + 1), j even, at once, one position per 16-bit half of a register.
+// `pairs[k]` holds the complemented heights (255 - tile[k]) | (255 - tile[k + 1]) << 16 of cell k and its right
+// neighbour, so the X*Y loads of a lane deliver the windows of both positions.  With g = 255 - h:
+//   window maximum        m = 255 - min g                          VIMNMX3.U16x2
+//   cell below maximum    t = min(g - min g, 1), kept as t + 256    VIADDMNMX.U16x2 (g + (256 - min g), 257)
+//   cells == maximum      cnt = X*Y - sum t;  corners below maximum cb = sum of the four corner t
+// and the three-way threshold rule of acktr/utils.py:28-33 becomes one comparison per half:
+//   feasible  <=>  cnt >= need(cb),  need = half | most | full for cb = 0 | 1 | >= 2
+//             <=>  cnt + max(0, b0 - cb * (b0 - b1)) >= full,   b0 = full - half, b1 = full - most   (needs b0 >= 2 * b1)
+// evaluated with a bias of 0x8000 per half so that bit 15 / bit 31 are the two answers and no borrow ever crosses
+// the halves.  Positions are enumerated in increasing cell index (pair, then half), like the scalar sweep.
+// ---------------------------------------------------------------------------------------------------
+template <int X, int Y, int CS>
+__device__ __forceinline__ int sweep_loop_packed(const uint32_t *pairs, uint8_t *smask, int zmax, int lane)
+{
+    constexpr int kNi = CS - X + 1, kNj = CS - Y + 1, kNpj = (kNj + 1) / 2, kWork = kNi * kNpj;
+    constexpr int a = X * Y, full = (19 * a) / 20 + 1, most = (17 * a) / 20 + 1, half = a / 2 + 1;
+    constexpr int b0 = full - half, b1 = full - most, K = b0 - b1;
+    static_assert(b0 >= 2 * b1 && b1 >= 0, "threshold spacing assumed by the clamped bonus");
+    constexpr uint32_t kRcp = (65536 + kNpj - 1) / kNpj;
+    constexpr uint32_t kOnes = 0x00010001u;
+    // t is carried with an offset of 256 per cell: sum t' = below + 256 a, cb' = cb + 1024
+    // v = cnt + bonus - full + 0x8000 = (a + b0 - full + 0x8000 + 256 a) - sum t' - min(cb K, b0)
+    //   with min(cb K, b0) = min(cb' K, b0 + 1024 K) - 1024 K
+    constexpr uint32_t kBase = (uint32_t)(a + b0 - full + 0x8000 + 256 * a + 1024 * K) * kOnes;
+    constexpr uint32_t kPenCap = (uint32_t)(b0 + 1024 * K) * kOnes;
+    static_assert(a + b0 - full + 0x8000 + 256 * a + 1024 * K < 0x10000 && 1028 * K < 0x10000, "16-bit halves");
+    // fits: m <= zmax  <=>  min g >= 255 - zmax  <=>  bit 15 of (min g + 0x8000 - 255 + zmax)
+    const uint32_t zc = (uint32_t)(0x8000 - 255 + zmax) * kOnes;
+    int mine = 0;
+#pragma unroll 1
+    for (int u0 = 0; u0 < kWork; u0 += 32) {
+        const int u = u0 + lane;
+        if (u < kWork) {
+            const int i = (int)(((uint32_t)u * kRcp) >> 16), jp = u - i * kNpj;
+            const int idx = i * CS + 2 * jp;
+            const uint32_t *w = pairs + idx;
+            uint32_t g[a];
+#pragma unroll
+            for (int r = 0; r < X; ++r)
+#pragma unroll
+                for (int c = 0; c < Y; ++c) g[r * Y + c] = w[r * CS + c];
+            uint32_t gm = g[0];
+#pragma unroll
+            for (int k = 1; k + 1 < a; k += 2) gm = __vimin3_u16x2(gm, g[k], g[k + 1]);
+            if ((a & 1) == 0) gm = __vminu2(gm, g[a - 1]);
+            const uint32_t neg = 0x01000100u - gm;                     // 256 - min g per half, in 1..256
+            uint32_t t[a];
+#pragma unroll
+            for (int k = 0; k < a; ++k) t[k] = __viaddmin_u16x2(g[k], neg, 0x01010101u);
+            uint32_t below = 0;
+#pragma unroll
+            for (int k = 0; k < a; ++k) below += t[k];
+            const uint32_t cb = t[0] + t[Y - 1] + t[(X - 1) * Y] + t[a - 1];
+            const uint32_t v = kBase - below - __vminu2(cb * (uint32_t)K, kPenCap);
+            const uint32_t f = gm + zc;
+            const uint32_t ok2 = v & f & (2 * jp + 1 < kNj ? 0x80008000u : 0x00008000u);
+            smask[idx] = (uint8_t)((ok2 >> 15) & 1u);
+            smask[idx + 1] = (uint8_t)(ok2 >> 31);                     // a non-candidate cell when j + 1 == nj: stays 0
+            mine += __popc(ok2);
+        }
+    }
+    return __reduce_add_sync(kFull, mine);
+}
+
+// pairs[k] = (255 - tile[k]) | (255 - tile[k + 1]) << 16 for the A cells of a tile (A % 4 == 0; the word after the
+// tile's last one must be readable: it only feeds the right neighbour of the last cell, which no valid position uses).
+__device__ __forceinline__ void build_pairs(const uint8_t *tile, uint32_t *pairs, int A, int lane)
+{
+    const uint32_t *t32 = reinterpret_cast<const uint32_t *>(tile);
+    uint4 *p4 = reinterpret_cast<uint4 *>(pairs);
+#pragma unroll 1
+    for (int k = lane; k < (A >> 2); k += 32) {
+        const uint32_t w0 = t32[k], w1 = t32[k + 1];
+        uint4 o;
+        o.x = 0x00ff00ffu - __byte_perm(w0, 0u, 0x4140);
+        o.y = 0x00ff00ffu - __byte_perm(w0, 0u, 0x4241);
+        o.z = 0x00ff00ffu - __byte_perm(w0, 0u, 0x4342);
+        o.w = 0x00ff00ffu - __byte_perm(__funnelshift_r(w0, w1, 24), 0u, 0x4140);   // last byte of w0, first of w1
+        p4[k] = o;
+    }
+}
+
 // Mask of one orientation: lanes sweep the (L-x+1)(W-y+1) candidate positions of the tile, write
 // smask[i*W+j] = feasible, and return the number of feasible positions (warp-uniform).
 // acktr/utils.py:54-57 / envs/bpp0/bin3D.py:85-88.  smask must be zero on entry; thr = pack_thresholds(x*y).
@@ -311,9 +441,11 @@ __device__ __forceinline__ int sweep_loop(const uint8_t *tile, uint8_t *smask, i
 // a 64 KB variant with two positions per lane ran 2x slower).  Anything else takes the generic loop.
 template <int VARIANT, int CS = 0>
 __device__ __forceinline__ int sweep_orientation(const uint8_t *tile, uint8_t *smask, int L, int W, int H,
-                                                 int x, int y, int z, uint32_t thr, int lane)
+                                                 int x, int y, int z, uint32_t thr, int lane,
+                                                 const uint32_t *pairs = nullptr)
 {
     if (x > L || y > W) return 0;                        // range(width - x + 1) empty, utils.py:54-55
+    if (z > H) return 0;                                 // max_h + z > H everywhere, utils.py:20-21
     const int zmax = pinned(H - z);                      // m + z <= H  <=>  m <= H - z
     const int nj = W - y + 1;
     const bool spec = x >= 2 && x <= 5 && y >= 2 && y <= 5;          // footprints with their own loop below
@@ -323,7 +455,8 @@ __device__ __forceinline__ int sweep_orientation(const uint8_t *tile, uint8_t *s
     const int thr_full = pinned((int)(thr & 1023u)), thr_most = pinned((int)((thr >> 10) & 1023u)),
               thr_half = pinned((int)(thr >> 20));
 #define BPP_SW_CASE(X, Y) case ((X) - 2) * 4 + ((Y) - 2): \
-        return sweep_loop<VARIANT, X, Y, CS>(tile, smask, W, x, y, npos, rcp, dW, thr_full, thr_most, thr_half, zmax, lane);
+        if constexpr (kPackedSweep && CS > 0 && VARIANT == 2) return sweep_loop_packed<X, Y, CS>(pairs, smask, zmax, lane); \
+        else return sweep_loop<VARIANT, X, Y, CS>(tile, smask, W, x, y, npos, rcp, dW, thr_full, thr_most, thr_half, zmax, lane);
 #define BPP_SW_ROW(X) BPP_SW_CASE(X, 2) BPP_SW_CASE(X, 3) BPP_SW_CASE(X, 4) BPP_SW_CASE(X, 5)
     if (spec) {
         switch ((x - 2) * 4 + (y - 2)) {

@@ -47,10 +47,12 @@ inline void derive_params(const bpp_config &cfg, EnvParams &p)
     }
 }
 
-// Dynamic shared memory of one step-kernel CTA: per warp the heightmap tile, the mask tile and 32 staged bin records.
+// Dynamic shared memory of one step-kernel CTA: per warp the heightmap tile, the mask tile, the packed sweep's pair
+// array (compile-time bin sides only) and 32 staged bin records.
 inline size_t step_smem_bytes(const EnvParams &p)
 {
-    return (size_t)kWarpsPerBlock * (size_t)(p.A_pad + p.M_pad) + (size_t)kWarpsPerBlock * 32 * 80;
+    const int cs = (p.L == p.W && (p.L == 10 || p.L == 20)) ? p.L : 0;
+    return (size_t)kWarpsPerBlock * (size_t)(p.A_pad + p.M_pad + pair_bytes(cs)) + (size_t)kWarpsPerBlock * 32 * 80;
 }
 
 }  // namespace bpp

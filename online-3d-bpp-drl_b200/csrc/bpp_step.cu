@@ -68,11 +68,15 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
     const int L = CS ? CS : p.L, W = CS ? CS : p.W, H = p.H, A = CS ? CS * CS : p.A;
     const int A_pad = CS ? ((CS * CS + 15) & ~15) : p.A_pad;
     const int M = A * (ROT ? 2 : 1), M_pad = CS ? ((CS * CS * (ROT ? 2 : 1) + 15) & ~15) : p.M_pad;
-    uint8_t *tile = smem + pinned(warp * (A_pad + M_pad));
+    // per warp: heightmap tile | mask tile | (packed-sweep builds) complemented height pairs, one word per cell
+    constexpr bool kPacked = kPackedSweep && CS > 0 && VARIANT == 2;
+    const int warp_bytes = A_pad + M_pad + pair_bytes(CS);
+    uint8_t *tile = smem + pinned(warp * warp_bytes);
     uint8_t *smask = tile + A_pad;
+    uint32_t *pairs = reinterpret_cast<uint32_t *>(tile + A_pad + M_pad);
     // per-warp record of the 32 bins of a batch: 20 words per bin, written in phase A, read in B and A2, so that
     // the per-lane scalars do not occupy registers during the tile work
-    uint4 *rec = reinterpret_cast<uint4 *>(smem + kWarpsPerBlock * (A_pad + M_pad)) + pinned(warp * (32 * kRecQuads));
+    uint4 *rec = reinterpret_cast<uint4 *>(smem + kWarpsPerBlock * warp_bytes) + pinned(warp * (32 * kRecQuads));
     uint4 *tile4 = reinterpret_cast<uint4 *>(tile);
     uint4 *smask4 = reinterpret_cast<uint4 *>(smask);
     const int nq_tile = A_pad >> 4, nq_mask = M_pad >> 4;     // 128-bit words per tile
@@ -128,6 +132,20 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                 if (lx + x <= L && ly + y <= W) {
                     act = (uint32_t)idx | ((uint32_t)x << 10) | ((uint32_t)y << 16) | (1u << 22);
                     thr_cur = pack_thresholds(x * y);
+                    if (kLaneCheck && x * y <= 32) {
+                        // Space.check_box (space.py:116-144) by this lane alone, on the bin's heightmap in global
+                        // memory (the sectors are re-read from L1 by the tile load of phase B).  The verdict and the
+                        // new height of the footprint replace the in-bounds flag: act bit 22 = placed,
+                        // bits 24..31 = max_h + z, bit 23 = decided here.
+                        const uint8_t *w = p.hm + (size_t)mybin * A_pad + idx;
+                        const int z = (s.box >> 16) & 0xff;
+                        const int c00 = w[0], c10 = w[(x - 1) * W], c01 = w[y - 1], c11 = w[(x - 1) * W + y - 1];
+                        int m, cnt;
+                        if (y <= 5) window_stats_rows5<uint8_t>(w, W, x, y, m, cnt);
+                        else window_stats<uint8_t>(w, W, x, y, m, cnt);
+                        const bool ok = accept<1>(m, cnt, thr_cur, z, H, c00, c10, c01, c11);
+                        act = (act & 0x003fffffu) | (1u << 23) | (ok ? (1u << 22) | ((uint32_t)(m + z) << 24) : 0u);
+                    }
                 }
             }
         }
@@ -203,7 +221,15 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
 
             bool succ = false;
             if (mode == kModeStep) {
-                if (bact >> 22) {
+                if (kLaneCheck && (bact & (1u << 23))) {
+                    // decided in phase A: raise the footprint (update_height_graph, space.py:36-46)
+                    succ = (bact >> 22) & 1u;
+                    if (succ) {
+                        const int x = (bact >> 10) & 63, y = (bact >> 16) & 63, a = x * y;
+                        const int r = (int)(((uint32_t)lane * rcp16((uint32_t)y)) >> 16);
+                        if (lane < a) tile[(bact & 1023u) + r * (W - y) + lane] = (uint8_t)(bact >> 24);
+                    }
+                } else if ((bact >> 22) & 1u) {
                     // Space.check_box (space.py:116-144) with the lanes spread over the footprint
                     const int x = (bact >> 10) & 63, y = (bact >> 16) & 63, z = (box >> 16) & 0xff;
                     uint8_t *w = tile + (bact & 1023u);
@@ -261,9 +287,13 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             const int bx = nbox & 0xff, by = (nbox >> 8) & 0xff, bz = (nbox >> 16) & 0xff;
             int total = 0;
             if (w_mask || w_sample) {
+                if (kPacked) {
+                    build_pairs(tile, pairs, A, lane);
+                    __syncwarp();
+                }
 #pragma unroll 1
                 for (int o = 0; o < (ROT ? 2 : 1); ++o)
-                    total += sweep_orientation<VARIANT, CS>(tile, smask + o * A, L, W, H, o ? by : bx, o ? bx : by, bz, nthr, lane);
+                    total += sweep_orientation<VARIANT, CS>(tile, smask + o * A, L, W, H, o ? by : bx, o ? bx : by, bz, nthr, lane, pairs);
                 __syncwarp();
             }
 

@@ -81,7 +81,7 @@ def _ptr(a):
 def _aligned(shape, dtype, fill=0):
     """16-byte aligned array (the kernels use 128-bit accesses on rows)."""
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
-    raw = np.zeros(n + 64, dtype=np.uint8)
+    raw = np.zeros(n + 128, dtype=np.uint8)       # >= 64 readable bytes after the array (kHmSlack)
     off = (-raw.ctypes.data) % 64
     a = raw[off:off + n].view(dtype).reshape(shape)
     a[...] = fill

@@ -216,6 +216,39 @@ static inline float __fdiv_rn(float a, float b) { return a / b; }       // IEEE 
 static inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 
+// 16-bit-pair integer instructions (VIMNMX.U16x2, VIMNMX3.U16x2, VIADDMNMX.U16x2), PRMT and SHF.R
+static inline uint32_t __vminu2(uint32_t a, uint32_t b)
+{
+    return std::min(a & 0xffffu, b & 0xffffu) | (std::min(a >> 16, b >> 16) << 16);
+}
+static inline uint32_t __vmaxu2(uint32_t a, uint32_t b)
+{
+    return std::max(a & 0xffffu, b & 0xffffu) | (std::max(a >> 16, b >> 16) << 16);
+}
+static inline uint32_t __vimin3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vminu2(__vminu2(a, b), c); }
+static inline uint32_t __vimax3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vmaxu2(__vmaxu2(a, b), c); }
+static inline uint32_t __viaddmin_u16x2(uint32_t a, uint32_t b, uint32_t c)
+{
+    const uint32_t lo = ((a & 0xffffu) + (b & 0xffffu)) & 0xffffu, hi = ((a >> 16) + (b >> 16)) & 0xffffu;   // halves wrap
+    return std::min(lo, c & 0xffffu) | (std::min(hi, c >> 16) << 16);
+}
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s)
+{
+    const uint64_t src = (uint64_t)x | ((uint64_t)y << 32);
+    uint32_t r = 0;
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t n = (s >> (4 * k)) & 0xfu;
+        uint32_t b = (uint32_t)(src >> (8 * (n & 7u))) & 0xffu;
+        if (n & 8u) b = (b & 0x80u) ? 0xffu : 0u;          // sign replication mode
+        r |= b << (8 * k);
+    }
+    return r;
+}
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift)
+{
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> (shift & 31u));
+}
+
 static inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_exchange(0); }
 static inline void __syncthreads() { simt::yield(simt::WAIT_BLOCK); }
 static inline void need_full(unsigned mask) { if (mask != 0xffffffffu) simt::die("only full-mask collectives are emulated"); }

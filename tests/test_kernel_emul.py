@@ -18,8 +18,10 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "sim
 import emul   # noqa: E402
 
 
-def _okw(gen_kw):
-    return dict(gen_kw)
+# kernel build variants (online-3d-bpp-drl_b200/build.py -D...): the default build and the one with the packed
+# 16-bit-pair mask sweep + the lane-per-bin placement check
+FULL = ("BPP_PACKED_SWEEP=1", "BPP_LANE_CHECK=1")
+VARIANTS = [pytest.param((), id="default"), pytest.param(FULL, id="packed+lanecheck")]
 
 
 def run_against_oracle(N, size, rot, variant, gen_kw, T, seed, offset=0, global_n=None, edge_every=0, num_sms=2,
@@ -55,30 +57,46 @@ def run_against_oracle(N, size, rot, variant, gen_kw, T, seed, offset=0, global_
     return e.metrics_dict()
 
 
+@pytest.mark.parametrize("defines", VARIANTS)
 @pytest.mark.parametrize("rot,variant", [(False, 2), (True, 2), (True, 1)])
-def test_step_kernel_rs_10cube(rot, variant):
+def test_step_kernel_rs_10cube(rot, variant, defines):
     # the compile-time 10x10 fast path (CS = 10, FAST), 32-bin warp batches with a ragged tail, several batches per warp
     m = run_against_oracle(300, (10, 10, 10), rot, variant, dict(gen="rs"), T=24, seed=1234, edge_every=7, offset=77,
-                           global_n=4096)
+                           global_n=4096, defines=defines)
     assert m["episodes"] > 300
 
 
-def test_step_kernel_20cube_and_small_batches():
+@pytest.mark.parametrize("defines", VARIANTS)
+def test_step_kernel_20cube_and_small_batches(defines):
     # CS = 20; few bins on "many SMs" -> the batch-size rule picks fewer bins per warp
-    run_against_oracle(40, (20, 20, 20), False, 2, dict(gen="rs"), T=40, seed=99, num_sms=8, blocks_per_sm=2)
+    run_against_oracle(40, (20, 20, 20), False, 2, dict(gen="rs"), T=40, seed=99, num_sms=8, blocks_per_sm=2, defines=defines)
 
 
-def test_step_kernel_generic_sizes():
+@pytest.mark.parametrize("defines", VARIANTS)
+def test_step_kernel_generic_sizes(defines):
     # CS = 0: scalar stores (L*W % 4 != 0), non-square bin, items larger than the bin, footprints outside 2..5
     items = np.array([(x, y, z) for x in (1, 3, 8) for y in (2, 7) for z in (1, 4)], dtype=np.uint8)
-    run_against_oracle(70, (7, 9, 6), True, 1, dict(gen="rs", item_set=items), T=30, seed=3, edge_every=4)
-    run_against_oracle(33, (8, 12, 9), False, 2, dict(gen="rs"), T=30, seed=4)      # vec4 generic path
+    run_against_oracle(70, (7, 9, 6), True, 1, dict(gen="rs", item_set=items), T=30, seed=3, edge_every=4, defines=defines)
+    run_against_oracle(33, (8, 12, 9), False, 2, dict(gen="rs"), T=30, seed=4, defines=defines)      # vec4 generic path
 
 
-def test_step_kernel_replay_rotation(golden_dir):
+@pytest.mark.parametrize("defines", VARIANTS)
+def test_step_kernel_tall_bins_and_items_that_never_fit(defines):
+    # heights up to 255 (16-bit halves of the packed sweep keep their head room), items taller than the bin, footprints
+    # with a side of 1 or > 5 next to the specialised 2..5 ones, rows of more than 5 cells in the lane-per-bin check
+    items = np.array([(x, y, z) for x in (2, 3, 5) for y in (2, 4, 5) for z in (1, 37, 90, 200)], dtype=np.uint8)
+    run_against_oracle(64, (10, 10, 255), True, 2, dict(gen="rs", item_set=items), T=30, seed=5, defines=defines)
+    items = np.array([(x, y, z) for x in (1, 2, 4, 6) for y in (1, 3, 5, 6) for z in (1, 3, 6, 8)], dtype=np.uint8)
+    run_against_oracle(64, (10, 10, 5), True, 2, dict(gen="rs", item_set=items), T=30, seed=6, edge_every=4, defines=defines)
+    items = np.array([(x, y, z) for x in (2, 5) for y in (3, 4) for z in (1, 60, 99)], dtype=np.uint8)
+    run_against_oracle(24, (20, 20, 200), True, 2, dict(gen="rs", item_set=items), T=30, seed=7, defines=defines)
+
+
+@pytest.mark.parametrize("defines", VARIANTS)
+def test_step_kernel_replay_rotation(golden_dir, defines):
     d = np.load(os.path.join(golden_dir, "datasets.npz"))
     run_against_oracle(96, (10, 10, 10), True, 2, dict(gen="replay", traj=d["cut_2"], traj_len=d["cut_2_len"], first_traj=1),
-                       T=40, seed=8, offset=3 * 65536, global_n=524288, edge_every=5)
+                       T=40, seed=8, offset=3 * 65536, global_n=524288, edge_every=5, defines=defines)
 
 
 @pytest.mark.parametrize("kind,rot", [("cut1", True), ("cut2", False)])
@@ -87,7 +105,8 @@ def test_cut_generators(kind, rot):
     run_against_oracle(40, (10, 10, 10), rot, 2, dict(gen=kind), T=30, seed=31, offset=5000, global_n=100000, edge_every=9)
 
 
-def test_golden_rollout_through_the_interpreted_kernel(golden_dir):
+@pytest.mark.parametrize("defines", VARIANTS)
+def test_golden_rollout_through_the_interpreted_kernel(golden_dir, defines):
     """The reference's own trace (recorded from the Python reference) replayed through the kernel source."""
     g = np.load(os.path.join(golden_dir, "ref_rollouts_10_rot.npz"))
     size, rot = tuple(int(v) for v in g["size"]), bool(g["rot"])
@@ -96,7 +115,7 @@ def test_golden_rollout_through_the_interpreted_kernel(golden_dir):
     A = size[0] * size[1]
     for variant in (1, 2):
         e = emul.EmulEnv(N, size, rot=rot, mask_variant=variant, gen="replay", traj=g["traj"], traj_len=g["traj_len"],
-                         first_traj=0)
+                         first_traj=0, defines=defines)
         want = g["mask_v1"] if variant == 1 else g["mask_v2"]
         e.reset()
         for t in range(T):
@@ -108,9 +127,10 @@ def test_golden_rollout_through_the_interpreted_kernel(golden_dir):
             assert np.max(np.abs(e.ratio.astype(np.float64) - g["ratio"][t])) <= 1e-6
 
 
-def test_partial_outputs_and_observe():
+@pytest.mark.parametrize("defines", VARIANTS)
+def test_partial_outputs_and_observe(defines):
     """Null output pointers (the non-FAST instantiation) and bpp_observe leave the state and the other outputs intact."""
-    e = emul.EmulEnv(64, (10, 10, 10), seed=5)
+    e = emul.EmulEnv(64, (10, 10, 10), seed=5, defines=defines)
     o = orc.OracleEnv(64, (10, 10, 10), seed=5)
     e.reset(); o.reset()
     for t in range(6):
