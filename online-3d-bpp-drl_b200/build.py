@@ -15,6 +15,23 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
 
 
+# Named kernel build variants (csrc/bpp_common.cuh): tools/ab_bench.py times them against the default build on a B200;
+# tests/test_kernel_emul.py checks them bit for bit on the CPU.  Built next to the default as b200bpp/variants/*.so.
+VARIANTS = {
+    "packed": ["BPP_PACKED_SWEEP=1"],
+    "lanecheck": ["BPP_LANE_CHECK=1"],
+    "full": ["BPP_PACKED_SWEEP=1", "BPP_LANE_CHECK=1", "BPP_SQUARE_COPY=1"],
+}
+
+
+def variant_path(name):
+    return os.path.join(HERE, "b200bpp", "variants", "libbpp_b200_%s.so" % name)
+
+
+def build_variants(names=None, verbose=False):
+    return [build(out=variant_path(n), defines=VARIANTS[n], verbose=verbose) for n in (names or sorted(VARIANTS))]
+
+
 def nvcc():
     for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
@@ -45,6 +62,9 @@ def build(force=False, verbose=False, out=None, defines=()):
 
 
 if __name__ == "__main__":
+    if "--variants" in sys.argv:
+        print("\n".join(build_variants(verbose="-v" in sys.argv)))
+        sys.exit(0)
     defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
     outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=os.path.abspath(outs[0]) if outs else None,

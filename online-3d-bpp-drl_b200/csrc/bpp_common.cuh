@@ -40,6 +40,12 @@ constexpr bool kPackedSweep = BPP_PACKED_SWEEP != 0;
 #define BPP_LANE_CHECK 0
 #endif
 constexpr bool kLaneCheck = BPP_LANE_CHECK != 0;
+// Build variant: with rotation enabled, an item with x == y has two identical orientations (acktr/utils.py:76-88 computes
+// the same mask twice); the second half of the mask is then a copy of the first instead of a second sweep.
+#ifndef BPP_SQUARE_COPY
+#define BPP_SQUARE_COPY 0
+#endif
+constexpr bool kSquareCopy = BPP_SQUARE_COPY != 0;
 // bytes of the per-warp "pairs" array that the packed sweep reads (one 32-bit word per heightmap cell)
 __host__ __device__ constexpr int pair_bytes(int cs) { return kPackedSweep && cs > 0 ? 4 * ((cs * cs + 15) & ~15) : 0; }
 

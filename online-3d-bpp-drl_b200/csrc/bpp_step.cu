@@ -291,9 +291,20 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                     build_pairs(tile, pairs, A, lane);
                     __syncwarp();
                 }
+                if (kSquareCopy && ROT && VEC4 && bx == by) {
+                    // both orientations are the same footprint: sweep once, copy the half (A % 4 == 0 under VEC4)
+                    total = sweep_orientation<VARIANT, CS>(tile, smask, L, W, H, bx, by, bz, nthr, lane, pairs);
+                    __syncwarp();
+                    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(smask);
+                    uint32_t *d32 = reinterpret_cast<uint32_t *>(smask + A);
 #pragma unroll 1
-                for (int o = 0; o < (ROT ? 2 : 1); ++o)
-                    total += sweep_orientation<VARIANT, CS>(tile, smask + o * A, L, W, H, o ? by : bx, o ? bx : by, bz, nthr, lane, pairs);
+                    for (int k = lane; k < (A >> 2); k += 32) d32[k] = s32[k];
+                    total *= 2;
+                } else {
+#pragma unroll 1
+                    for (int o = 0; o < (ROT ? 2 : 1); ++o)
+                        total += sweep_orientation<VARIANT, CS>(tile, smask + o * A, L, W, H, o ? by : bx, o ? bx : by, bz, nthr, lane, pairs);
+                }
                 __syncwarp();
             }
 

@@ -19,9 +19,9 @@ import emul   # noqa: E402
 
 
 # kernel build variants (online-3d-bpp-drl_b200/build.py -D...): the default build and the one with the packed
-# 16-bit-pair mask sweep + the lane-per-bin placement check
-FULL = ("BPP_PACKED_SWEEP=1", "BPP_LANE_CHECK=1")
-VARIANTS = [pytest.param((), id="default"), pytest.param(FULL, id="packed+lanecheck")]
+# 16-bit-pair mask sweep + the lane-per-bin placement check + the single sweep for square items under rotation
+FULL = ("BPP_PACKED_SWEEP=1", "BPP_LANE_CHECK=1", "BPP_SQUARE_COPY=1")
+VARIANTS = [pytest.param((), id="default"), pytest.param(FULL, id="packed+lanecheck+squarecopy")]
 
 
 def run_against_oracle(N, size, rot, variant, gen_kw, T, seed, offset=0, global_n=None, edge_every=0, num_sms=2,
