@@ -21,6 +21,8 @@ VARIANTS = {
     "packed": ["BPP_PACKED_SWEEP=1"],
     "lanecheck": ["BPP_LANE_CHECK=1"],
     "full": ["BPP_PACKED_SWEEP=1", "BPP_LANE_CHECK=1", "BPP_SQUARE_COPY=1"],
+    "psq": ["BPP_PACKED_SWEEP=1", "BPP_SQUARE_COPY=1"],
+    "fullps": ["BPP_PACKED_SWEEP=1", "BPP_LANE_CHECK=1", "BPP_SQUARE_COPY=1", "BPP_PLAIN_STORES=1"],
 }
 
 

@@ -46,6 +46,28 @@ constexpr bool kLaneCheck = BPP_LANE_CHECK != 0;
 #define BPP_SQUARE_COPY 0
 #endif
 constexpr bool kSquareCopy = BPP_SQUARE_COPY != 0;
+// Build variant: observation / mask rows leave with ordinary write-back stores instead of streaming (evict-first) ones,
+// so that a consumer launched right after the step (the policy network) and the next step's overwrite find them in L2.
+#ifndef BPP_PLAIN_STORES
+#define BPP_PLAIN_STORES 0
+#endif
+#if BPP_PLAIN_STORES && !defined(BPP_SIMT_EMUL)
+// stated in PTX: the output pointers went through pinned_ptr(), a plain C++ store would become a generic ST
+__device__ __forceinline__ void store_out(float4 *p, float4 v)
+{
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void store_out(float *p, float v)
+{
+    asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+#else
+template <typename T>
+__device__ __forceinline__ void store_out(T *p, T v)
+{
+    __stcs(p, v);
+}
+#endif
 // bytes of the per-warp "pairs" array that the packed sweep reads (one 32-bit word per heightmap cell)
 __host__ __device__ constexpr int pair_bytes(int cs) { return kPackedSweep && cs > 0 ? 4 * ((cs * cs + 15) & ~15) : 0; }
 

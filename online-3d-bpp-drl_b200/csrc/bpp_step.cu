@@ -291,19 +291,19 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                     build_pairs(tile, pairs, A, lane);
                     __syncwarp();
                 }
-                if (kSquareCopy && ROT && VEC4 && bx == by) {
-                    // both orientations are the same footprint: sweep once, copy the half (A % 4 == 0 under VEC4)
-                    total = sweep_orientation<VARIANT, CS>(tile, smask, L, W, H, bx, by, bz, nthr, lane, pairs);
+                // with rotation, an item with x == y has two identical orientations: sweep once and copy the half
+                // (one call site for both cases: the specialised sweep loops must not be duplicated in the binary)
+                const bool square = kSquareCopy && ROT && VEC4 && bx == by;
+#pragma unroll 1
+                for (int o = 0; o < (ROT ? (square ? 1 : 2) : 1); ++o)
+                    total += sweep_orientation<VARIANT, CS>(tile, smask + o * A, L, W, H, o ? by : bx, o ? bx : by, bz, nthr, lane, pairs);
+                if (square) {
                     __syncwarp();
                     const uint32_t *s32 = reinterpret_cast<const uint32_t *>(smask);
                     uint32_t *d32 = reinterpret_cast<uint32_t *>(smask + A);
 #pragma unroll 1
                     for (int k = lane; k < (A >> 2); k += 32) d32[k] = s32[k];
                     total *= 2;
-                } else {
-#pragma unroll 1
-                    for (int o = 0; o < (ROT ? 2 : 1); ++o)
-                        total += sweep_orientation<VARIANT, CS>(tile, smask + o * A, L, W, H, o ? by : bx, o ? bx : by, bz, nthr, lane, pairs);
                 }
                 __syncwarp();
             }
@@ -321,16 +321,16 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                     const uint32_t *t32 = reinterpret_cast<const uint32_t *>(tile);
 #pragma unroll 1
                     for (int k = lane; k < q4; k += 32) {
-                        __stcs(o4 + k, bytes_to_float4(t32[k]));
-                        __stcs(o4 + q4 + k, plane_lut[bx]);
-                        __stcs(o4 + 2 * q4 + k, plane_lut[by]);
-                        __stcs(o4 + 3 * q4 + k, plane_lut[bz]);
+                        store_out(o4 + k, bytes_to_float4(t32[k]));
+                        store_out(o4 + q4 + k, plane_lut[bx]);
+                        store_out(o4 + 2 * q4 + k, plane_lut[by]);
+                        store_out(o4 + 3 * q4 + k, plane_lut[bz]);
                     }
                 } else {
 #pragma unroll 1
                     for (int k = lane; k < A; k += 32) {
-                        __stcs(o + k, (float)tile[k]); __stcs(o + A + k, fx);
-                        __stcs(o + 2 * A + k, fy); __stcs(o + 3 * A + k, fz);
+                        store_out(o + k, (float)tile[k]); store_out(o + A + k, fx);
+                        store_out(o + 2 * A + k, fy); store_out(o + 3 * A + k, fz);
                     }
                 }
             }
@@ -341,10 +341,10 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                     const uint32_t *s32 = reinterpret_cast<const uint32_t *>(smask);
 #pragma unroll 1
                     for (int k = lane; k < (M >> 2); k += 32)
-                        __stcs(m4 + k, total == 0 ? make_float4(1.f, 1.f, 1.f, 1.f) : bytes_to_float4(s32[k]));
+                        store_out(m4 + k, total == 0 ? make_float4(1.f, 1.f, 1.f, 1.f) : bytes_to_float4(s32[k]));
                 } else {
 #pragma unroll 1
-                    for (int k = lane; k < M; k += 32) __stcs(mo + k, total == 0 ? 1.f : (float)smask[k]);
+                    for (int k = lane; k < M; k += 32) store_out(mo + k, total == 0 ? 1.f : (float)smask[k]);
                 }
             }
             uint32_t pick = 0;

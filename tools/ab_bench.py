@@ -115,6 +115,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--rounds", type=int, default=3)
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--bw", action="store_true", help="also time write-only / read-only / copy streams (1 GiB, torch kernels)")
     args = ap.parse_args()
     import torch
     import bench
@@ -122,6 +123,29 @@ def main():
     torch.cuda.set_device(dev)
     libs = [(s.split("=", 1)[0], bind(s.split("=", 1)[1])) for s in args.libs]
     results = {}
+    if args.bw:
+        # what a write-dominated kernel can hope for: the step kernel writes 13x more than it reads, while the roofline
+        # denominator (MEASURED_PEAKS.json) is a copy, i.e. half reads
+        n = 1 << 28
+        a = torch.empty(n, dtype=torch.float32, device=dev)
+        b = torch.empty(n, dtype=torch.float32, device=dev)
+        a.fill_(1.0); b.fill_(2.0)
+        st = torch.cuda.current_stream(dev)
+
+        def best_ms(fn, reps=6):
+            t = float("inf")
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st); fn(); e1.record(st)
+                torch.cuda.synchronize(dev)
+                t = min(t, e0.elapsed_time(e1))
+            return t
+        gb = n * 4 / 1e9
+        bw = {"write_only_GBps": gb / (best_ms(lambda: a.fill_(3.0)) * 1e-3),
+              "read_only_GBps": gb / (best_ms(lambda: a.sum()) * 1e-3),
+              "copy_GBps": 2 * gb / (best_ms(lambda: b.copy_(a)) * 1e-3), "bytes": n * 4}
+        print(json.dumps({"bandwidth": bw}), flush=True)
+        del a, b
     for wl in args.workloads:
         bins, size, rot, gen, desc = bench.WORKLOADS[wl]
         envs = []
