@@ -15,14 +15,13 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
 
 
-# Named kernel build variants (csrc/bpp_common.cuh): tools/ab_bench.py times them against the default build on a B200;
+# Named kernel build variants (switches in csrc/bpp_common.cuh): tools/ab_bench.py times them against the default build on a B200;
 # tests/test_kernel_emul.py checks them bit for bit on the CPU.  Built next to the default as b200bpp/variants/*.so.
 VARIANTS = {
-    "packed": ["BPP_PACKED_SWEEP=1"],
-    "lanecheck": ["BPP_LANE_CHECK=1"],
-    "full": ["BPP_PACKED_SWEEP=1", "BPP_LANE_CHECK=1", "BPP_SQUARE_COPY=1"],
-    "psq": ["BPP_PACKED_SWEEP=1", "BPP_SQUARE_COPY=1"],
-    "fullps": ["BPP_PACKED_SWEEP=1", "BPP_LANE_CHECK=1", "BPP_SQUARE_COPY=1", "BPP_PLAIN_STORES=1"],
+    # every switch off: the kernel as it stood before the packed sweep / lane check / square copy / plain stores
+    "baseline": ["BPP_PACKED_SWEEP=0", "BPP_LANE_CHECK=0", "BPP_SQUARE_COPY=0", "BPP_PLAIN_STORES=0"],
+    "packed": ["BPP_PACKED_SWEEP=1", "BPP_LANE_CHECK=0", "BPP_SQUARE_COPY=0", "BPP_PLAIN_STORES=0"],
+    "streaming": ["BPP_PLAIN_STORES=0"],          # the default build with streaming (evict-first) output stores
 }
 
 

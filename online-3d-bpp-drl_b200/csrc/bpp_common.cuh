@@ -27,29 +27,30 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kMaxSide = 32;          // L, W <= 32 (reciprocal-multiply position decode, smem tile)
 constexpr unsigned kFull = 0xffffffffu;
 
-// Build variant: the mask sweep of the compile-time bin sizes evaluates TWO candidate positions per lane with the
+// Build switch (on by default; -DBPP_PACKED_SWEEP=0 gives the round-1 scalar sweep for A/B runs, tools/ab_bench.py):
+// the mask sweep of the compile-time bin sizes evaluates TWO candidate positions per lane with the
 // 16-bit-pair integer instructions (VIMNMX3.U16x2, VIADDMNMX.U16x2); see sweep_loop_packed below.
 #ifndef BPP_PACKED_SWEEP
-#define BPP_PACKED_SWEEP 0
+#define BPP_PACKED_SWEEP 1
 #endif
 constexpr bool kPackedSweep = BPP_PACKED_SWEEP != 0;
-// Build variant: the placement check of step() (Space.check_box at the chosen position) runs in the lane-per-bin phase
+// Build switch (on by default): the placement check of step() (Space.check_box at the chosen position) runs in the lane-per-bin phase
 // straight from the heightmap in global memory for footprints of up to 32 cells; the warp-per-bin phase then only
 // raises the footprint.  Larger footprints (the (10,10,10) sentinels) keep the warp-cooperative check.
 #ifndef BPP_LANE_CHECK
-#define BPP_LANE_CHECK 0
+#define BPP_LANE_CHECK 1
 #endif
 constexpr bool kLaneCheck = BPP_LANE_CHECK != 0;
-// Build variant: with rotation enabled, an item with x == y has two identical orientations (acktr/utils.py:76-88 computes
+// Build switch (on by default): with rotation enabled, an item with x == y has two identical orientations (acktr/utils.py:76-88 computes
 // the same mask twice); the second half of the mask is then a copy of the first instead of a second sweep.
 #ifndef BPP_SQUARE_COPY
-#define BPP_SQUARE_COPY 0
+#define BPP_SQUARE_COPY 1
 #endif
 constexpr bool kSquareCopy = BPP_SQUARE_COPY != 0;
-// Build variant: observation / mask rows leave with ordinary write-back stores instead of streaming (evict-first) ones,
+// Build switch (on by default): observation / mask rows leave with ordinary write-back stores instead of streaming (evict-first) ones,
 // so that a consumer launched right after the step (the policy network) and the next step's overwrite find them in L2.
 #ifndef BPP_PLAIN_STORES
-#define BPP_PLAIN_STORES 0
+#define BPP_PLAIN_STORES 1
 #endif
 #if BPP_PLAIN_STORES && !defined(BPP_SIMT_EMUL)
 // stated in PTX: the output pointers went through pinned_ptr(), a plain C++ store would become a generic ST

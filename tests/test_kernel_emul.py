@@ -18,10 +18,11 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "sim
 import emul   # noqa: E402
 
 
-# kernel build variants (online-3d-bpp-drl_b200/build.py -D...): the default build and the one with the packed
-# 16-bit-pair mask sweep + the lane-per-bin placement check + the single sweep for square items under rotation
-FULL = ("BPP_PACKED_SWEEP=1", "BPP_LANE_CHECK=1", "BPP_SQUARE_COPY=1")
-VARIANTS = [pytest.param((), id="default"), pytest.param(FULL, id="packed+lanecheck+squarecopy")]
+# kernel builds (switches in csrc/bpp_common.cuh, online-3d-bpp-drl_b200/build.py -D...): the default one (packed
+# 16-bit-pair mask sweep, lane-per-bin placement check, single sweep for square items under rotation) and the one with
+# every switch off, which tools/ab_bench.py keeps as the timing baseline
+BASELINE = ("BPP_PACKED_SWEEP=0", "BPP_LANE_CHECK=0", "BPP_SQUARE_COPY=0", "BPP_PLAIN_STORES=0")
+VARIANTS = [pytest.param((), id="default"), pytest.param(BASELINE, id="baseline")]
 
 
 def run_against_oracle(N, size, rot, variant, gen_kw, T, seed, offset=0, global_n=None, edge_every=0, num_sms=2,
