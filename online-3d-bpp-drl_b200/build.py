@@ -22,6 +22,7 @@ VARIANTS = {
     "baseline": ["BPP_PACKED_SWEEP=0", "BPP_LANE_CHECK=0", "BPP_SQUARE_COPY=0", "BPP_PLAIN_STORES=0"],
     "packed": ["BPP_PACKED_SWEEP=1", "BPP_LANE_CHECK=0", "BPP_SQUARE_COPY=0", "BPP_PLAIN_STORES=0"],
     "streaming": ["BPP_PLAIN_STORES=0"],          # the default build with streaming (evict-first) output stores
+    "split": ["BPP_PAIRS_SPLIT=1"],               # next candidate: bank-conflict-free layout of the packed sweep's pairs
 }
 
 

@@ -34,6 +34,14 @@ constexpr unsigned kFull = 0xffffffffu;
 #define BPP_PACKED_SWEEP 1
 #endif
 constexpr bool kPackedSweep = BPP_PACKED_SWEEP != 0;
+// Build switch (off until measured): the pair words of even and odd cells live in two separate halves of the pairs
+// array.  A lane's pair of positions starts at an even cell, so for a given window cell all lanes of a load read
+// cells of one parity: interleaved, they fall on every other bank (3-way conflicts at 10x10, ncu: 7.5 M conflicts per
+// launch); split, on consecutive banks.
+#ifndef BPP_PAIRS_SPLIT
+#define BPP_PAIRS_SPLIT 0
+#endif
+constexpr bool kPairsSplit = BPP_PAIRS_SPLIT != 0;
 // Build switch (on by default): the placement check of step() (Space.check_box at the chosen position) runs in the lane-per-bin phase
 // straight from the heightmap in global memory for footprints of up to 32 cells; the warp-per-bin phase then only
 // raises the footprint.  Larger footprints (the (10,10,10) sentinels) keep the warp-cooperative check.
@@ -414,12 +422,22 @@ __device__ __forceinline__ int sweep_loop_packed(const uint32_t *pairs, uint8_t 
         if (u < kWork) {
             const int i = (int)(((uint32_t)u * kRcp) >> 16), jp = u - i * kNpj;
             const int idx = i * CS + 2 * jp;
-            const uint32_t *w = pairs + idx;
             uint32_t g[a];
+            if (kPairsSplit) {
+                // cell idx + d sits in half (d & 1) at word (idx >> 1) + (d >> 1); idx is even
+                constexpr int kHalf = ((CS * CS + 15) & ~15) / 2;
+                const uint32_t *w = pairs + (idx >> 1);
 #pragma unroll
-            for (int r = 0; r < X; ++r)
+                for (int r = 0; r < X; ++r)
 #pragma unroll
-                for (int c = 0; c < Y; ++c) g[r * Y + c] = w[r * CS + c];
+                    for (int c = 0; c < Y; ++c) g[r * Y + c] = w[((r * CS + c) & 1) * kHalf + ((r * CS + c) >> 1)];
+            } else {
+                const uint32_t *w = pairs + idx;
+#pragma unroll
+                for (int r = 0; r < X; ++r)
+#pragma unroll
+                    for (int c = 0; c < Y; ++c) g[r * Y + c] = w[r * CS + c];
+            }
             uint32_t gm = g[0];
 #pragma unroll
             for (int k = 1; k + 1 < a; k += 2) gm = __vimin3_u16x2(gm, g[k], g[k + 1]);
@@ -457,7 +475,14 @@ __device__ __forceinline__ void build_pairs(const uint8_t *tile, uint32_t *pairs
         o.y = 0x00ff00ffu - __byte_perm(w0, 0u, 0x4241);
         o.z = 0x00ff00ffu - __byte_perm(w0, 0u, 0x4342);
         o.w = 0x00ff00ffu - __byte_perm(__funnelshift_r(w0, w1, 24), 0u, 0x4140);   // last byte of w0, first of w1
-        p4[k] = o;
+        if (kPairsSplit) {        // cells 4k, 4k+2 -> even half words 2k, 2k+1; cells 4k+1, 4k+3 -> odd half
+            const int half = ((A + 15) & ~15) >> 1;
+            uint2 *e2 = reinterpret_cast<uint2 *>(pairs), *o2 = reinterpret_cast<uint2 *>(pairs + half);
+            e2[k] = make_uint2(o.x, o.z);
+            o2[k] = make_uint2(o.y, o.w);
+        } else {
+            p4[k] = o;
+        }
     }
 }
 
