@@ -2,11 +2,12 @@
 //
 // One launch per env step.  Persistent CTAs of 8 warps; every warp takes batches of 32 bins through three phases
 // (details at the kernel): scalar work with one LANE per bin, heightmap-tile work with the whole WARP per bin
-// (128-bit staged u8 tile in shared memory, placement check with warp reductions, mask sweep with one lane per
-// candidate position and the footprint unrolled at compile time, 128-bit streaming stores of the float32 observation
-// and mask), and the per-bin results again with one lane per bin.
-// HBM-bound integer work by design (no tensor cores); in practice instruction-issue limited, see DESIGN.md section 3
-// and profiles/README.md.  Reference behaviour is cited inline (paths relative to the reference root).
+// (128-bit staged u8 tile in shared memory, footprint update, mask sweep with two candidate positions per lane in
+// 16-bit register halves and the footprint unrolled at compile time, 128-bit stores of the float32 observation and
+// mask), and the per-bin results again with one lane per bin.
+// HBM-bound integer work by design (no tensor cores); in practice latency-bound at 32 resident warps per SM (66 % issue
+// utilisation, DRAM at 56 %), see DESIGN.md section 3 and profiles/README.md.  Reference behaviour is cited inline
+// (paths relative to the reference root).
 #include <cstdlib>
 
 #include "bpp_common.cuh"
@@ -44,10 +45,11 @@ __device__ __forceinline__ uint32_t episode_item(const EnvParams &p, long long b
 // The kernel works on batches of 32 bins per warp (fewer for small N) in three phases:
 //   A  (lane = bin)   scalar work once per bin instead of once per lane: state record, action decode with bounds
 //                     test, Philox draws, both candidates for the next item (placement succeeds / episode ends) and
-//                     their count thresholds; everything is staged as an 80-byte record per bin in shared memory;
+//                     their count thresholds, the placement check itself for footprints of up to 32 cells (read from
+//                     global memory); everything is staged as an 80-byte record per bin in shared memory;
 //   B  (warp = bin)   for each bin of the batch in turn: record (two broadcast 128-bit loads), heightmap tile
-//                     (prefetched one bin ahead), placement check + update, mask sweep, tile / observation / mask
-//                     write-back, action sampling;
+//                     (prefetched one bin ahead), footprint update (warp-cooperative check for larger footprints),
+//                     mask sweep, tile / observation / mask write-back, action sampling;
 //   A2 (lane = bin)   reward, done, info, new state record, coalesced stores, episode metrics, generator refill list.
 //
 // Template parameters: ROT = enable_rotation, VARIANT = mask rule, VEC4 = 128-bit output stores possible,
