@@ -168,3 +168,21 @@ def test_stateless_kernels_fuzz(size):
     for variant in (1, 2):
         want = np.array([orc.check_box(plain[b], q[b, 0], q[b, 1], q[b, 2], q[b, 3], q[b, 4], size, variant) for b in range(n)])
         assert np.array_equal(emul.check_box(plain, q, size, variant), want)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_small_configurations(seed):
+    """Seeded random bin sizes / item sets / rules / rotation / generators through the generic (CS = 0) instantiations and,
+    when the draw lands on them, the compile-time ones; ragged N, several launches' worth of batches."""
+    rng = np.random.default_rng(1000 + seed)
+    L, W = (int(v) for v in rng.integers(3, 13, 2))
+    if seed % 3 == 0:
+        L = W = 10                                   # the compile-time path with odd item sets
+    H = int(rng.integers(4, 40))
+    n_items = int(rng.integers(1, 9))
+    items = np.stack([rng.integers(1, max(2, L // 2 + 2), n_items), rng.integers(1, max(2, W // 2 + 2), n_items),
+                      rng.integers(1, max(2, H // 2 + 1), n_items)], 1).astype(np.uint8)
+    rot, variant = bool(rng.integers(0, 2)), int(rng.integers(1, 3))
+    N = int(rng.integers(1, 90))
+    run_against_oracle(N, (L, W, H), rot, variant, dict(gen="rs", item_set=items), T=12, seed=seed, edge_every=5,
+                       num_sms=int(rng.integers(1, 4)), blocks_per_sm=int(rng.integers(1, 3)))
