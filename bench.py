@@ -354,6 +354,7 @@ def main():
             "config": {"workload": desc, "bins_per_gpu": N, "total_bins": total_bins, "container": list(size),
                        "rotation": rot, "generator": gen, "mask_variant": "v2 (acktr.utils.check_box)",
                        "policy": "uniform-random valid action, sampled in the step kernel",
+                       "build": lib.bpp_build_info().decode(),
                        "parallelism": "bins sharded %d-way, no data-path collective" % world,
                        "l2": "per-step working set %.0f MB per GPU vs 126 MB L2 (inputs larger than L2, no flush)"
                              % (N * (b_alg) / 1e6)},

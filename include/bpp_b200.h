@@ -80,6 +80,8 @@ int32_t bpp_abi_version(void);
 const char *bpp_last_error(void);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 uint64_t bpp_launch_count(void);
+/* The build switches this library was compiled with ("packed_sweep=1 lane_check=1 ..."), for bench provenance. */
+const char *bpp_build_info(void);
 
 /* -- lifetime: replaces gym.make('Bpp-v0', ...) x N in acktr/envs.py:31-41,86-101 ---------------- */
 int32_t bpp_create(const bpp_config *cfg, bpp_env **out);

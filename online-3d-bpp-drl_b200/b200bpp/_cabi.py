@@ -41,6 +41,7 @@ SYMBOLS = {
     "bpp_abi_version": (_i32, []),
     "bpp_last_error": (C.c_char_p, []),
     "bpp_launch_count": (C.c_uint64, []),
+    "bpp_build_info": (C.c_char_p, []),
     "bpp_create": (_i32, [C.POINTER(Config), C.POINTER(_vp)]),
     "bpp_destroy": (_i32, [_vp]),
     "bpp_reset": (_i32, [_vp, _vp, _vp, _vp, _vp]),

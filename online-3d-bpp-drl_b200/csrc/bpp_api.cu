@@ -95,6 +95,15 @@ int32_t bpp_abi_version(void) { return BPP_ABI_VERSION; }
 const char *bpp_last_error(void) { return g_last_error.c_str(); }
 uint64_t bpp_launch_count(void) { return g_launches.load(); }
 
+#define BPP_STR2(x) #x
+#define BPP_STR(x) BPP_STR2(x)
+const char *bpp_build_info(void)
+{
+    return "packed_sweep=" BPP_STR(BPP_PACKED_SWEEP) " lane_check=" BPP_STR(BPP_LANE_CHECK) " square_copy=" BPP_STR(BPP_SQUARE_COPY)
+           " plain_stores=" BPP_STR(BPP_PLAIN_STORES) " pairs_split=" BPP_STR(BPP_PAIRS_SPLIT)
+           " warps_per_block=" BPP_STR(BPP_WARPS_PER_BLOCK) " sm_100a";
+}
+
 int32_t bpp_destroy(bpp_env *env)
 {
     if (!env) return BPP_OK;

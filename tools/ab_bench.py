@@ -173,7 +173,8 @@ def main():
         results[wl] = {name: {"ms_per_step": best[name], "env_steps_per_s": bins / (best[name] * 1e-3),
                               "roofline_frac": bins * bench.algorithmic_bytes(size, rot) / (best[name] * 1e-3) / 1e9
                               / bench.hbm_peak()[0],
-                              "metrics": met[name], "metrics_equal_to_first": met[name] == ref} for name, _ in envs}
+                              "metrics": met[name], "metrics_equal_to_first": met[name] == ref,
+                              "build": dict(libs)[name].bpp_build_info().decode()} for name, _ in envs}
         print(json.dumps({wl: results[wl]}), flush=True)
     return 0
 
