@@ -23,6 +23,8 @@ VARIANTS = {
     "packed": ["BPP_PACKED_SWEEP=1", "BPP_LANE_CHECK=0", "BPP_SQUARE_COPY=0", "BPP_PLAIN_STORES=0"],
     "streaming": ["BPP_PLAIN_STORES=0"],          # the default build with streaming (evict-first) output stores
     "split": ["BPP_PAIRS_SPLIT=1"],               # next candidate: bank-conflict-free layout of the packed sweep's pairs
+    "occ5": ["BPP_MIN_BLOCKS=5"],                 # 48 registers, 40 warps per SM (spills ~110 B per thread: re-measure)
+    "split_occ5": ["BPP_PAIRS_SPLIT=1", "BPP_MIN_BLOCKS=5"],
 }
 
 
