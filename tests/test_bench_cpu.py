@@ -34,3 +34,16 @@ def test_algorithmic_bytes_match_survey():
     assert bench.algorithmic_bytes((10, 10, 10), False) == 2825
     assert bench.algorithmic_bytes((10, 10, 10), True) == 3225
     assert bench.algorithmic_bytes((20, 20, 20), False) == 11225
+
+
+def test_ab_picker_on_the_recorded_sessions():
+    """tools/ab_pick.py names the build with the best geometric-mean step time over the workloads (profiles/r1k_ab_*.jsonl
+    are the two A/B sessions of round 1)."""
+    import subprocess
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    pick = lambda f: subprocess.check_output([sys.executable, os.path.join(root, "tools", "ab_pick.py"),
+                                              os.path.join(root, "profiles", f)]).decode().strip()
+    assert pick("r1k_ab_first.jsonl") == "packed"        # before the square copy had a single call site
+    assert pick("r1k_ab_final.jsonl") == "fullps"        # = today's default build
+    assert pick("does_not_exist.jsonl") == "full"
