@@ -22,7 +22,11 @@ VARIANTS = {
     "baseline": ["BPP_PACKED_SWEEP=0", "BPP_LANE_CHECK=0", "BPP_SQUARE_COPY=0", "BPP_PLAIN_STORES=0"],
     "packed": ["BPP_PACKED_SWEEP=1", "BPP_LANE_CHECK=0", "BPP_SQUARE_COPY=0", "BPP_PLAIN_STORES=0"],
     "streaming": ["BPP_PLAIN_STORES=0"],          # the default build with streaming (evict-first) output stores
-    "split": ["BPP_PAIRS_SPLIT=1"],               # next candidate: bank-conflict-free layout of the packed sweep's pairs
+    # candidates that cut load/store-unit work (bit-exact under tests/test_kernel_emul.py, not yet timed):
+    "split": ["BPP_PAIRS_SPLIT=1"],               # bank-conflict-free layout of the packed sweep's pairs
+    "nolut": ["BPP_PLANE_LUT=0"],                 # observation planes converted in registers instead of 3 LDS.128
+    "words": ["BPP_LANE_CHECK_WORDS=1"],          # lane-per-bin check: 2 aligned word loads per row instead of 5 bytes
+    "lsu": ["BPP_PAIRS_SPLIT=1", "BPP_PLANE_LUT=0", "BPP_LANE_CHECK_WORDS=1"],
     "occ5": ["BPP_MIN_BLOCKS=5"],                 # 48 registers, 40 warps per SM (spills ~110 B per thread: re-measure)
     "split_occ5": ["BPP_PAIRS_SPLIT=1", "BPP_MIN_BLOCKS=5"],
 }

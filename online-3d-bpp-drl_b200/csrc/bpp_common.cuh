@@ -5,6 +5,7 @@
 #pragma once
 
 #include <cstdint>
+#include <cstddef>
 #ifdef BPP_SIMT_EMUL
 // tests/simt/simt_emul.h: the no-GPU test suite interprets these kernel sources lane by lane on the CPU (tests only;
 // the library itself is always built by nvcc for sm_100a and has no CPU path)
@@ -38,6 +39,13 @@ constexpr bool kPackedSweep = BPP_PACKED_SWEEP != 0;
 // array.  A lane's pair of positions starts at an even cell, so for a given window cell all lanes of a load read
 // cells of one parity: interleaved, they fall on every other bank (3-way conflicts at 10x10, ncu: 7.5 M conflicts per
 // launch); split, on consecutive banks.
+// Build switch (on = round-1 behaviour): the constant x / y / z planes of the observation come from a shared-memory
+// table of (v, v, v, v) rows -- three broadcast LDS.128 per bin, 6 shared-memory wavefronts -- instead of three
+// int-to-float conversions.  Saves issue slots, costs load/store-unit bandwidth; 0 = convert in registers.
+#ifndef BPP_PLANE_LUT
+#define BPP_PLANE_LUT 1
+#endif
+constexpr bool kPlaneLut = BPP_PLANE_LUT != 0;
 #ifndef BPP_PAIRS_SPLIT
 #define BPP_PAIRS_SPLIT 0
 #endif
@@ -298,6 +306,39 @@ __device__ __forceinline__ void window_stats_rows5(const T *w, int W, int x, int
             const int v = (int)row[c];
             h[c] = c < y ? v : -1;
         }
+        const int rm = max(max(max(h[0], h[1]), max(h[2], h[3])), h[4]);
+        int below = 0;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) below += min(rm - h[c], 1);
+        const int rc = 5 - below;
+        cnt = rm > m ? rc : cnt + (rm == m ? rc : 0);
+        m = max(m, rm);
+    }
+}
+
+// Same again, with the 5 cells of a row taken from the two aligned 32-bit words that contain them (2 global loads per
+// row instead of 5 byte loads: the lane-per-bin check costs load/store-unit requests, 32 different sectors per
+// instruction).  Reads up to 7 bytes past the row's first cell.  Build switch BPP_LANE_CHECK_WORDS (off until measured).
+#ifndef BPP_LANE_CHECK_WORDS
+#define BPP_LANE_CHECK_WORDS 0
+#endif
+constexpr bool kLaneCheckWords = BPP_LANE_CHECK_WORDS != 0;
+__device__ __forceinline__ void window_stats_rows5_words(const uint8_t *w, int W, int x, int y, int &m, int &cnt)
+{
+    m = -1;
+    cnt = 0;
+#pragma unroll 1
+    for (int r = 0; r < x; ++r) {
+        const uint8_t *row = w + r * W;
+        const uint32_t sh = ((uint32_t)(uintptr_t)row & 3u) * 8u;
+        const uint32_t *aw = reinterpret_cast<const uint32_t *>(row - (sh >> 3));
+        const uint32_t w0 = aw[0], w1 = aw[1];
+        const uint32_t lo = __funnelshift_r(w0, w1, sh);          // cells 0..3 of the row
+        int h[5];
+        h[0] = (int)(lo & 0xffu); h[1] = (int)((lo >> 8) & 0xffu); h[2] = (int)((lo >> 16) & 0xffu); h[3] = (int)(lo >> 24);
+        h[4] = (int)((w1 >> sh) & 0xffu);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) h[c] = c < y ? h[c] : -1;
         const int rm = max(max(max(h[0], h[1]), max(h[2], h[3])), h[4]);
         int below = 0;
 #pragma unroll

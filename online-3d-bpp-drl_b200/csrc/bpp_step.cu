@@ -143,7 +143,11 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                         const int z = (s.box >> 16) & 0xff;
                         const int c00 = w[0], c10 = w[(x - 1) * W], c01 = w[y - 1], c11 = w[(x - 1) * W + y - 1];
                         int m, cnt;
+#if BPP_LANE_CHECK_WORDS
+                        if (y <= 5) window_stats_rows5_words(w, W, x, y, m, cnt);
+#else
                         if (y <= 5) window_stats_rows5<uint8_t>(w, W, x, y, m, cnt);
+#endif
                         else window_stats<uint8_t>(w, W, x, y, m, cnt);
                         const bool ok = accept<1>(m, cnt, thr_cur, z, H, c00, c10, c01, c11);
                         act = (act & 0x003fffffu) | (1u << 23) | (ok ? (1u << 22) | ((uint32_t)(m + z) << 24) : 0u);
@@ -324,9 +328,9 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
 #pragma unroll 1
                     for (int k = lane; k < q4; k += 32) {
                         store_out(o4 + k, bytes_to_float4(t32[k]));
-                        store_out(o4 + q4 + k, plane_lut[bx]);
-                        store_out(o4 + 2 * q4 + k, plane_lut[by]);
-                        store_out(o4 + 3 * q4 + k, plane_lut[bz]);
+                        store_out(o4 + q4 + k, kPlaneLut ? plane_lut[bx] : make_float4(fx, fx, fx, fx));
+                        store_out(o4 + 2 * q4 + k, kPlaneLut ? plane_lut[by] : make_float4(fy, fy, fy, fy));
+                        store_out(o4 + 3 * q4 + k, kPlaneLut ? plane_lut[bz] : make_float4(fz, fz, fz, fz));
                     }
                 } else {
 #pragma unroll 1

@@ -22,7 +22,9 @@ import emul   # noqa: E402
 # 16-bit-pair mask sweep, lane-per-bin placement check, single sweep for square items under rotation) and the one with
 # every switch off, which tools/ab_bench.py keeps as the timing baseline
 BASELINE = ("BPP_PACKED_SWEEP=0", "BPP_LANE_CHECK=0", "BPP_SQUARE_COPY=0", "BPP_PLAIN_STORES=0")
-SPLIT = ("BPP_PAIRS_SPLIT=1",)          # candidate not yet timed on a B200: even / odd pair words in separate halves
+# candidates not yet timed on a B200 (build variant "lsu"): even / odd pair words in separate halves, observation planes
+# converted in registers, word loads in the lane-per-bin check
+SPLIT = ("BPP_PAIRS_SPLIT=1", "BPP_PLANE_LUT=0", "BPP_LANE_CHECK_WORDS=1")
 VARIANTS = [pytest.param((), id="default"), pytest.param(BASELINE, id="baseline")]
 
 
@@ -59,7 +61,7 @@ def run_against_oracle(N, size, rot, variant, gen_kw, T, seed, offset=0, global_
     return e.metrics_dict()
 
 
-@pytest.mark.parametrize("defines", VARIANTS + [pytest.param(SPLIT, id="split-pairs")])
+@pytest.mark.parametrize("defines", VARIANTS + [pytest.param(SPLIT, id="lsu-candidates")])
 @pytest.mark.parametrize("rot,variant", [(False, 2), (True, 2), (True, 1)])
 def test_step_kernel_rs_10cube(rot, variant, defines):
     # the compile-time 10x10 fast path (CS = 10, FAST), 32-bin warp batches with a ragged tail, several batches per warp
@@ -68,7 +70,7 @@ def test_step_kernel_rs_10cube(rot, variant, defines):
     assert m["episodes"] > 300
 
 
-@pytest.mark.parametrize("defines", VARIANTS + [pytest.param(SPLIT, id="split-pairs")])
+@pytest.mark.parametrize("defines", VARIANTS + [pytest.param(SPLIT, id="lsu-candidates")])
 def test_step_kernel_20cube_and_small_batches(defines):
     # CS = 20; few bins on "many SMs" -> the batch-size rule picks fewer bins per warp
     run_against_oracle(40, (20, 20, 20), False, 2, dict(gen="rs"), T=40, seed=99, num_sms=8, blocks_per_sm=2, defines=defines)

@@ -6,7 +6,7 @@ cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}" || exit 1
 mkdir -p gpurun_out
 V=online-3d-bpp-drl_b200/b200bpp
 LIBS="default=$V/libbpp_b200.so"
-for n in ${AB_VARIANTS:-baseline streaming split occ5 split_occ5}; do
+for n in ${AB_VARIANTS:-baseline split nolut words lsu occ5}; do
     [ -f "$V/variants/libbpp_b200_$n.so" ] && LIBS="$LIBS $n=$V/variants/libbpp_b200_$n.so"
 done
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,noheader > gpurun_out/ab_gpu.txt 2>&1
