@@ -5,8 +5,8 @@
 // (128-bit staged u8 tile in shared memory, footprint update, mask sweep with two candidate positions per lane in
 // 16-bit register halves and the footprint unrolled at compile time, 128-bit stores of the float32 observation and
 // mask), and the per-bin results again with one lane per bin.
-// HBM-bound integer work by design (no tensor cores); in practice latency-bound at 32 resident warps per SM (66 % issue
-// utilisation, DRAM at 56 %), see DESIGN.md section 3 and profiles/README.md.  Reference behaviour is cited inline
+// HBM-bound integer work by design (no tensor cores); in practice the L1 / shared-memory path is the busiest unit (72 %;
+// issue slots 66 %, DRAM 56 %), see DESIGN.md section 3 and profiles/README.md.  Reference behaviour is cited inline
 // (paths relative to the reference root).
 #include <cstdlib>
 
