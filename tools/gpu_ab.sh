@@ -9,6 +9,14 @@ LIBS="default=$V/libbpp_b200.so"
 for n in ${AB_VARIANTS:-baseline split nolut words lsu occ5}; do
     [ -f "$V/variants/libbpp_b200_$n.so" ] && LIBS="$LIBS $n=$V/variants/libbpp_b200_$n.so"
 done
+# compute-sanitizer over every kernel family of the default build (AB_SANITIZE=1; ~1 min per tool)
+if [ -n "$AB_SANITIZE" ]; then
+    for tool in memcheck racecheck; do
+        timeout 150 compute-sanitizer --tool $tool python tools/sanitize_smoke.py > gpurun_out/sanitizer_$tool.log 2>&1
+        echo "$tool exit $?" >> gpurun_out/sanitizer_$tool.log
+        tail -2 gpurun_out/sanitizer_$tool.log
+    done
+fi
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,noheader > gpurun_out/ab_gpu.txt 2>&1
 timeout "${AB_TIMEOUT:-170}" python tools/ab_bench.py --libs $LIBS --workloads ${AB_WORKLOADS:-target target_rot cfg3 cfg4} \
     --steps "${AB_STEPS:-200}" --rounds "${AB_ROUNDS:-3}" --bw > gpurun_out/ab.jsonl 2> gpurun_out/ab.err
