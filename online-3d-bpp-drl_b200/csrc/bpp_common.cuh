@@ -46,6 +46,13 @@ constexpr bool kPackedSweep = BPP_PACKED_SWEEP != 0;
 #define BPP_PLANE_LUT 1
 #endif
 constexpr bool kPlaneLut = BPP_PLANE_LUT != 0;
+// Build switch (off until measured): two batch sizes per launch.  16 384 batches of 32 bins over 4 736 resident warps
+// are 3.46 batches per warp, i.e. 4 rounds for some warps and 3 for the others; with the switch the launch runs whole
+// rounds of 2^bpw_log2-bin batches and then ONE round of smaller batches that every warp takes part in
+// (choose_batches() in bpp_params.h).
+#ifndef BPP_TWO_TIER
+#define BPP_TWO_TIER 0
+#endif
 #ifndef BPP_PAIRS_SPLIT
 #define BPP_PAIRS_SPLIT 0
 #endif
@@ -106,6 +113,10 @@ enum Mode : int { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
 struct EnvParams {
     int N, L, W, H, A, A_pad, M, M_pad;      // M = A * (1 + rot): mask length
     int bpw_log2;                            // log2(bins per warp batch), chosen per launch
+#if BPP_TWO_TIER
+    long long n_full;                        // batches of 2^bpw_log2 bins (whole rounds over the resident warps) ...
+    int tail_log2;                           // ... followed by one round of batches of 2^tail_log2 bins
+#endif
     int gen_kind;
     int n_items;
     const uint32_t *item_set;                // packed x | y<<8 | z<<16

@@ -12,6 +12,7 @@
 
 #include "bpp_common.cuh"
 #include "bpp_launch.h"
+#include "bpp_params.h"
 
 #ifndef BPP_MIN_BLOCKS
 #define BPP_MIN_BLOCKS 4   // resident CTAs per SM the register allocator must allow (8 warps each)
@@ -97,11 +98,22 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
     // bins per warp batch: 32 when there are plenty of bins, fewer (power of two) for small N so that the
     // batches still spread over all SMs instead of serialising 32 bins on a few warps
     const int bpw_log2 = p.bpw_log2;
+#if BPP_TWO_TIER
+    const long long n_full = p.n_full, full_bins = n_full << bpw_log2;
+    const long long n_batches = n_full + (((long long)p.N - full_bins + (1 << p.tail_log2) - 1) >> p.tail_log2);
+#else
     const long long n_batches = ((long long)p.N + (1 << bpw_log2) - 1) >> bpw_log2;
+#endif
     for (long long batch = (long long)blockIdx.x * kWarpsPerBlock + warp; batch < n_batches;
          batch += (long long)gridDim.x * kWarpsPerBlock) {
+#if BPP_TWO_TIER
+        const int blog = batch < n_full ? bpw_log2 : p.tail_log2;
+        const long long bin0 = batch < n_full ? batch << bpw_log2 : full_bins + ((batch - n_full) << p.tail_log2);
+        const int nb = (int)min((long long)(1 << blog), (long long)p.N - bin0);
+#else
         const long long bin0 = batch << bpw_log2;
         const int nb = (int)min((long long)(1 << bpw_log2), (long long)p.N - bin0);
+#endif
         const bool have = lane < nb;
         const long long mybin = have ? bin0 + lane : bin0;
         const unsigned long long gid = p.global_offset + (unsigned long long)mybin;
@@ -488,7 +500,13 @@ static cudaError_t launch_t(const EnvParams &p, const StepIO &io, int mode, int 
         static const char *force = std::getenv("BPP_BPW_LOG2");
         if (force && force[0] >= '0' && force[0] <= '5') q.bpw_log2 = force[0] - '0';
     }
+#if BPP_TWO_TIER
+    const BatchPlan plan = choose_batches(p.N, cap * kWarpsPerBlock);
+    q.bpw_log2 = plan.full_log2; q.n_full = plan.n_full; q.tail_log2 = plan.tail_log2;
+    const long long batches = plan.n_full + plan.n_tail;
+#else
     const long long batches = ((long long)p.N + (1 << q.bpw_log2) - 1) >> q.bpw_log2;
+#endif
     const long long want = (batches + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int grid = (int)(want < cap ? want : cap);
     BPP_LAUNCH((bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST>), grid, kThreads, smem, st, q, io, mode);

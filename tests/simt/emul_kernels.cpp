@@ -118,4 +118,11 @@ int emul_import_state(const bpp_config *cfg, const EmulBuffers *b, const int32_t
 
 unsigned long long emul_collectives(void) { return simt::M.collectives; }
 
+// choose_batches() of bpp_params.h (the BPP_TWO_TIER launch rule): out = {full_log2, tail_log2, n_full, n_tail}
+void emul_choose_batches(long long N, long long warps, long long *out)
+{
+    const BatchPlan b = choose_batches(N, warps);
+    out[0] = b.full_log2; out[1] = b.tail_log2; out[2] = b.n_full; out[3] = b.n_tail;
+}
+
 }  // extern "C"

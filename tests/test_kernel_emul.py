@@ -188,3 +188,26 @@ def test_random_small_configurations(seed):
     N = int(rng.integers(1, 90))
     run_against_oracle(N, (L, W, H), rot, variant, dict(gen="rs", item_set=items), T=12, seed=seed, edge_every=5,
                        num_sms=int(rng.integers(1, 4)), blocks_per_sm=int(rng.integers(1, 3)))
+
+
+TWO_TIER = ("BPP_TWO_TIER=1",)         # candidate not yet timed on a B200 (build variant "tier")
+
+
+def test_two_tier_batch_plan():
+    """choose_batches(): whole rounds of large batches, then one round of small ones; every bin exactly once."""
+    assert emul.choose_batches(1 << 19, 4736) == (5, 4, 3 * 4736, 4352)       # target: 3 rounds of 32 + one of 16 (was 4 of 32)
+    assert emul.choose_batches(262144, 4736) == (4, 3, 3 * 4736, 4352)        # configs[3]: 3 x 16 + 8 (was 2 x 32)
+    assert emul.choose_batches(65536, 4736)[1:] == (4, 0, 4096)               # configs[2]: one round of 16, as before
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        N, warps = int(rng.integers(1, 3_000_000)), int(rng.integers(1, 6000))
+        fl, tl, n_full, n_tail = emul.choose_batches(N, warps)
+        assert 0 <= tl <= fl <= 5 and n_full % warps == 0 and n_tail <= warps
+        rest = N - (n_full << fl)
+        assert 0 <= rest <= n_tail << tl and (n_tail == 0 or rest > (n_tail - 1) << tl)
+
+
+@pytest.mark.parametrize("n,num_sms,bps", [(300, 2, 1), (777, 1, 2), (40, 8, 2), (1000, 3, 1)])
+def test_two_tier_batches_through_the_kernel(n, num_sms, bps):
+    run_against_oracle(n, (10, 10, 10), True, 2, dict(gen="rs"), T=10, seed=n, edge_every=4, num_sms=num_sms, blocks_per_sm=bps,
+                       defines=TWO_TIER)
