@@ -26,6 +26,9 @@ BASELINE = ("BPP_PACKED_SWEEP=0", "BPP_LANE_CHECK=0", "BPP_SQUARE_COPY=0", "BPP_
 # converted in registers, word loads in the lane-per-bin check
 SPLIT = ("BPP_PAIRS_SPLIT=1", "BPP_PLANE_LUT=0", "BPP_LANE_CHECK_WORDS=1")
 VARIANTS = [pytest.param((), id="default"), pytest.param(BASELINE, id="baseline")]
+# the candidates are not shipped: their tests (two more g++ builds of the kernels, ~2 min) run with BPP_TEST_CANDIDATES=1
+candidates = pytest.mark.skipif(os.environ.get("BPP_TEST_CANDIDATES", "") != "1",
+                                reason="kernel candidates for the next A/B session: set BPP_TEST_CANDIDATES=1")
 
 
 def run_against_oracle(N, size, rot, variant, gen_kw, T, seed, offset=0, global_n=None, edge_every=0, num_sms=2,
@@ -61,7 +64,7 @@ def run_against_oracle(N, size, rot, variant, gen_kw, T, seed, offset=0, global_
     return e.metrics_dict()
 
 
-@pytest.mark.parametrize("defines", VARIANTS + [pytest.param(SPLIT, id="lsu-candidates")])
+@pytest.mark.parametrize("defines", VARIANTS + [pytest.param(SPLIT, id="lsu-candidates", marks=candidates)])
 @pytest.mark.parametrize("rot,variant", [(False, 2), (True, 2), (True, 1)])
 def test_step_kernel_rs_10cube(rot, variant, defines):
     # the compile-time 10x10 fast path (CS = 10, FAST), 32-bin warp batches with a ragged tail, several batches per warp
@@ -70,7 +73,7 @@ def test_step_kernel_rs_10cube(rot, variant, defines):
     assert m["episodes"] > 300
 
 
-@pytest.mark.parametrize("defines", VARIANTS + [pytest.param(SPLIT, id="lsu-candidates")])
+@pytest.mark.parametrize("defines", VARIANTS + [pytest.param(SPLIT, id="lsu-candidates", marks=candidates)])
 def test_step_kernel_20cube_and_small_batches(defines):
     # CS = 20; few bins on "many SMs" -> the batch-size rule picks fewer bins per warp
     run_against_oracle(40, (20, 20, 20), False, 2, dict(gen="rs"), T=40, seed=99, num_sms=8, blocks_per_sm=2, defines=defines)
@@ -207,6 +210,7 @@ def test_two_tier_batch_plan():
         assert 0 <= rest <= n_tail << tl and (n_tail == 0 or rest > (n_tail - 1) << tl)
 
 
+@candidates
 @pytest.mark.parametrize("n,num_sms,bps", [(300, 2, 1), (777, 1, 2), (40, 8, 2), (1000, 3, 1)])
 def test_two_tier_batches_through_the_kernel(n, num_sms, bps):
     run_against_oracle(n, (10, 10, 10), True, 2, dict(gen="rs"), T=10, seed=n, edge_every=4, num_sms=num_sms, blocks_per_sm=bps,
