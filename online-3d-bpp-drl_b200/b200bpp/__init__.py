@@ -10,3 +10,4 @@ from . import utils   # noqa: F401
 from .bpp0 import PackingGame   # noqa: F401,E402
 from . import rollout, dist   # noqa: F401,E402
 from .policy import PackingPolicy, greedy_policy   # noqa: F401,E402
+from . import lookahead   # noqa: F401,E402
