@@ -215,3 +215,11 @@ def test_two_tier_batch_plan():
 def test_two_tier_batches_through_the_kernel(n, num_sms, bps):
     run_against_oracle(n, (10, 10, 10), True, 2, dict(gen="rs"), T=10, seed=n, edge_every=4, num_sms=num_sms, blocks_per_sm=bps,
                        defines=TWO_TIER)
+
+
+def test_extreme_sizes():
+    """The largest bin the library accepts (32x32x255), single-bin and 33-bin envs (one full warp batch + one bin)."""
+    items = np.array([(1, 1, 1), (32, 32, 7), (5, 31, 200), (17, 2, 99), (3, 3, 255)], dtype=np.uint8)
+    run_against_oracle(1, (32, 32, 255), True, 2, dict(gen="rs", item_set=items), T=12, seed=1)
+    run_against_oracle(33, (32, 32, 255), False, 1, dict(gen="rs", item_set=items), T=8, seed=2, edge_every=3)
+    run_against_oracle(33, (1, 1, 1), True, 2, dict(gen="rs", item_set=np.array([(1, 1, 1)], dtype=np.uint8)), T=6, seed=3)
