@@ -1,7 +1,9 @@
 #!/bin/bash
 # One bounded GPU session (gpurun): time the kernel build variants against the default build, then run the GPU parity
 # suite on the fastest one.  Everything lands in gpurun_out/ as it is produced.
-#   /usr/local/graft/bin/gpurun --timeout 420 -- 'bash tools/gpu_ab.sh'
+#   python online-3d-bpp-drl_b200/build.py --variants        # HERE, before the call: nvcc cross-compiles without a GPU
+#   /usr/local/graft/bin/gpurun --timeout 420 -- 'AB_NCU=1 AB_SANITIZE=1 bash tools/gpu_ab.sh'
+# A session costs ~2.5 GPU-minutes of fixed overhead plus: A/B ~15 s, GPU suite ~35 s, ncu ~45 s, sanitizer ~2 min.
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}" || exit 1
 mkdir -p gpurun_out
 V=online-3d-bpp-drl_b200/b200bpp
