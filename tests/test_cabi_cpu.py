@@ -92,6 +92,15 @@ def test_product_never_imports_oracle():
                 assert "import oracle" not in text and "bpp_oracle" not in text and "from oracle" not in text, f
 
 
+def test_library_has_no_cpu_interpretation_inside(cabi):
+    """tests/simt/ compiles the kernel sources for the CPU *for tests*; nothing of it may end up in the product library."""
+    import subprocess
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", cabi.LIB_PATH]).decode()
+    assert "simt" not in syms and "emul" not in syms
+    exported = sorted(ln.split()[-1] for ln in syms.splitlines() if " T " in ln and "bpp_" in ln.split()[-1] and "_Z" not in ln)
+    assert exported == declared_symbols()          # the C ABI and nothing else with a bpp_ name
+
+
 def test_lazy_infos_and_spaces():
     import numpy as np
     from b200bpp.vec_env import LazyInfos, default_item_set, _pack_trajectories
