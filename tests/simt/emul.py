@@ -70,6 +70,8 @@ def lib(defines=()):
         l.emul_import_state.restype = C.c_int
         l.emul_import_state.argtypes = [C.POINTER(_cabi.Config), C.POINTER(_Buffers)] + [C.c_void_p] * 4
         l.emul_collectives.restype = C.c_uint64
+        l.emul_set_lane_order.restype = None
+        l.emul_set_lane_order.argtypes = [C.c_int]
         l.emul_choose_batches.restype = None
         l.emul_choose_batches.argtypes = [C.c_longlong, C.c_longlong, C.c_void_p]
         _libs[key] = l
@@ -246,3 +248,8 @@ def choose_batches(N, warps, defines=()):
     out = np.zeros(4, dtype=np.int64)
     lib(defines).emul_choose_batches(int(N), int(warps), _ptr(out))
     return tuple(int(v) for v in out)
+
+
+def set_lane_order(order, defines=()):
+    """0: lanes of a warp resume in order 0..31 between collectives, 1: 31..0, 2: odd lanes first."""
+    lib(defines).emul_set_lane_order(int(order))

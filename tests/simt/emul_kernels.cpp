@@ -12,6 +12,7 @@
 namespace simt {
 Machine M;
 int g_blocks_per_sm = 4;
+int g_lane_order = 0;
 }
 
 using namespace bpp;
@@ -117,6 +118,7 @@ int emul_import_state(const bpp_config *cfg, const EmulBuffers *b, const int32_t
 }
 
 unsigned long long emul_collectives(void) { return simt::M.collectives; }
+void emul_set_lane_order(int order) { simt::g_lane_order = order; }
 
 // choose_batches() of bpp_params.h (the BPP_TWO_TIER launch rule): out = {full_log2, tail_log2, n_full, n_tail}
 void emul_choose_batches(long long N, long long warps, long long *out)

@@ -87,6 +87,8 @@ struct Machine {
 
 extern Machine M;
 extern int g_blocks_per_sm;
+extern int g_lane_order;        // 0: lanes resume 0..31; 1: 31..0; 2: odd lanes first -- a missing __syncwarp() between a
+                                // shared-memory write and another lane's read survives at most one of these schedules
 
 [[noreturn]] static inline void die(const char *msg)
 {
@@ -157,10 +159,11 @@ static inline void run_block(int threads)
             if (wstate[w] == WAIT_BLOCK) continue;
             for (;;) {                                   // passes over the warp until it blocks or ends
                 State s = RUNNABLE;
-                for (int l = 0; l < 32; ++l) {
+                for (int k = 0; k < 32; ++k) {
+                    const int l = g_lane_order == 1 ? 31 - k : (g_lane_order == 2 ? ((k < 16 ? 2 * k + 1 : 2 * (k - 16))) : k);
                     Fiber &f = M.fibers[w * 32 + l];
                     resume(f);
-                    if (l == 0) s = f.state;
+                    if (k == 0) s = f.state;
                     else if (f.state != s) die("lanes of one warp diverged across a collective / barrier / exit");
                 }
                 if (s == WAIT_WARP) { ++M.collectives; continue; }

@@ -223,3 +223,22 @@ def test_extreme_sizes():
     run_against_oracle(1, (32, 32, 255), True, 2, dict(gen="rs", item_set=items), T=12, seed=1)
     run_against_oracle(33, (32, 32, 255), False, 1, dict(gen="rs", item_set=items), T=8, seed=2, edge_every=3)
     run_against_oracle(33, (1, 1, 1), True, 2, dict(gen="rs", item_set=np.array([(1, 1, 1)], dtype=np.uint8)), T=6, seed=3)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("defines", VARIANTS)
+def test_lane_schedule_does_not_matter(order, defines):
+    """Between two warp collectives the interpreter runs the lanes one after another; a shared-memory write that another
+    lane reads without a __syncwarp() in between would depend on that order.  Same results with the lanes reversed and
+    with the odd lanes first (step kernel with rotation, both generators, stateless masks)."""
+    emul.set_lane_order(order, defines)
+    try:
+        run_against_oracle(100, (10, 10, 10), True, 2, dict(gen="rs"), T=16, seed=21, edge_every=5, defines=defines)
+        run_against_oracle(40, (20, 20, 20), False, 1, dict(gen="rs"), T=10, seed=22, num_sms=4, defines=defines)
+        run_against_oracle(40, (7, 9, 6), True, 2, dict(gen="rs", item_set=np.array([(1, 2, 1), (3, 3, 2), (7, 2, 1)], np.uint8)),
+                           T=10, seed=23, defines=defines)
+        if not defines:
+            run_against_oracle(24, (10, 10, 10), True, 2, dict(gen="cut1"), T=12, seed=24)
+            run_against_oracle(24, (10, 10, 10), False, 2, dict(gen="cut2"), T=12, seed=25)
+    finally:
+        emul.set_lane_order(0, defines)
