@@ -28,6 +28,7 @@ VARIANTS = {
     "words": ["BPP_LANE_CHECK_WORDS=1"],          # lane-per-bin check: 2 aligned word loads per row instead of 5 bytes
     "lsu": ["BPP_PAIRS_SPLIT=1", "BPP_PLANE_LUT=0", "BPP_LANE_CHECK_WORDS=1"],
     "tier": ["BPP_TWO_TIER=1"],                   # whole rounds of large batches, then one round of small ones
+    "all": ["BPP_PAIRS_SPLIT=1", "BPP_PLANE_LUT=0", "BPP_LANE_CHECK_WORDS=1", "BPP_TWO_TIER=1"],
     "occ5": ["BPP_MIN_BLOCKS=5"],                 # 48 registers, 40 warps per SM (spills ~110 B per thread: re-measure)
     "split_occ5": ["BPP_PAIRS_SPLIT=1", "BPP_MIN_BLOCKS=5"],
 }

@@ -8,7 +8,7 @@ cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}" || exit 1
 mkdir -p gpurun_out
 V=online-3d-bpp-drl_b200/b200bpp
 LIBS="default=$V/libbpp_b200.so"
-for n in ${AB_VARIANTS:-baseline split nolut words lsu tier occ5}; do
+for n in ${AB_VARIANTS:-baseline split nolut words lsu tier all occ5}; do
     [ -f "$V/variants/libbpp_b200_$n.so" ] && LIBS="$LIBS $n=$V/variants/libbpp_b200_$n.so"
 done
 # compute-sanitizer over every kernel family of the default build (AB_SANITIZE=1; ~1 min per tool)
