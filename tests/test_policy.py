@@ -165,3 +165,31 @@ def test_policy_in_the_loop_on_device(gold):
         assert 0.60 < rb.mean() < 0.75                  # the reference reports 66.9 % for this model without lookahead
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+def test_rotation_model_live(golden_dir):
+    """`pretrained_models/rotation_cut_2.pt` (action space 2*L*W) through the restated network and through the reference's
+    `Policy`, on states of a recorded rotation rollout: same greedy actions, values and log-probabilities."""
+    import reference_loader as rl
+    REF = rl.load_reference()
+    if REF is None:
+        pytest.skip("reference tree not present (GPU box)")
+    from acktr.model import Policy
+    import gym
+    state, _ = torch.load(os.path.join(REF.path, "pretrained_models", "rotation_cut_2.pt"), map_location="cpu", weights_only=False)
+    pol = PackingPolicy((10, 10, 10), enable_rotation=True).load_reference_state(state)
+    args = types.SimpleNamespace(container_size=(10, 10, 10), enable_rotation=True, hidden_size=256, channel=4, pallet_size=10)
+    ref = Policy(obs_shape=(400,), action_space=gym.spaces.Discrete(200),
+                 base_kwargs={"recurrent": False, "hidden_size": 256, "args": args})
+    folded = {k.replace("module.", "").replace("add_bias.", "").replace("_bias", "bias"): v for k, v in state.items()}
+    ref.load_state_dict({k: (v.squeeze(-1) if v.dim() <= 3 else v) for k, v in folded.items()})      # model_loader.py:27-33
+    ref.eval()
+    g = np.load(os.path.join(golden_dir, "ref_rollouts_10_rot.npz"))
+    hm, box = g["hm"][:8].reshape(-1, 100), g["box"][:8].reshape(-1, 3)
+    obs = torch.from_numpy(np.concatenate([hm] + [np.repeat(box[:, c:c + 1], 100, 1) for c in range(3)], 1).astype(np.float32))
+    mask = torch.from_numpy(g["mask_v2"][:8].reshape(-1, 200).astype(np.float32))
+    with torch.no_grad():
+        v_ref, a_ref, lp_ref, _ = ref.act(obs, None, None, mask, deterministic=True)
+    v, a, lp = pol.act(obs, mask, deterministic=True)
+    assert torch.equal(a, a_ref) and int((a >= 100).sum()) > 0              # rotated placements do get chosen
+    assert torch.allclose(v, v_ref, rtol=1e-5, atol=1e-5) and torch.allclose(lp, lp_ref, rtol=1e-5, atol=1e-5)
