@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "b200bpp", "libbpp_b200.so")
 SOURCES = ["bpp_api.cu", "bpp_step.cu", "bpp_mask.cu", "bpp_gen.cu"]
-HEADERS = ["bpp_common.cuh", "bpp_launch.h", os.path.join("..", "..", "include", "bpp_b200.h")]
+HEADERS = ["bpp_common.cuh", "bpp_launch.h", "bpp_params.h", os.path.join("..", "..", "include", "bpp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
 
@@ -53,25 +53,36 @@ def nvcc():
     return "nvcc"
 
 
-def up_to_date():
-    if not os.path.exists(OUT):
+def _digest(defines=()):
+    """Content hash of sources, headers, flags and this script (mtimes lie after a `mv` or a `git checkout`)."""
+    import hashlib
+    h = hashlib.sha1((" ".join(NVCC_FLAGS) + "|" + " ".join(defines)).encode())
+    for f in SOURCES + HEADERS + [os.path.join("..", "build.py")]:
+        h.update(open(os.path.join(CSRC, f), "rb").read())
+    return h.hexdigest()
+
+
+def up_to_date(out=None, defines=()):
+    out = out or OUT
+    try:
+        return os.path.exists(out) and open(out + ".digest").read().strip() == _digest(defines)
+    except OSError:
         return False
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return all(os.path.getmtime(d) <= t for d in deps)
 
 
 def build(force=False, verbose=False, out=None, defines=()):
     """out/defines build an experimental variant (e.g. defines=["BPP_MIN_BLOCKS=6"]) next to the default."""
-    if out is None and not force and up_to_date():
-        return OUT
     out = out or OUT
+    if not force and up_to_date(out, defines):
+        return out
     os.makedirs(os.path.dirname(out), exist_ok=True)
     cmd = [nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
     env = dict(os.environ)
     env.pop("CC", None)      # the image exports a gcc wrapper in $CC that nvcc must not pick up
     env.pop("CXX", None)
     subprocess.check_call(cmd, cwd=CSRC, env=env)
+    with open(out + ".digest", "w") as f:
+        f.write(_digest(defines) + "\n")
     return out
 
 

@@ -16,24 +16,38 @@ from b200bpp import _cabi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.abspath(os.path.join(_HERE, "..", ".."))
 _CSRC = os.path.join(_ROOT, "online-3d-bpp-drl_b200", "csrc")
-_OUT = os.path.join(_HERE, "_build", "libbpp_emul.so")
 _DEPS = [os.path.join(_HERE, f) for f in ("simt_emul.h", "emul_kernels.cpp")] + \
         [os.path.join(_CSRC, f) for f in ("bpp_common.cuh", "bpp_launch.h", "bpp_params.h", "bpp_step.cu", "bpp_gen.cu",
                                           "bpp_mask.cu")] + [os.path.join(_ROOT, "include", "bpp_b200.h")]
 
 
+def _source_digest(defines):
+    """Content hash of everything the build depends on (mtimes lie after a `mv` or a `git checkout`)."""
+    import hashlib
+    h = hashlib.sha1(("|".join(defines)).encode())
+    for d in _DEPS:
+        h.update(open(d, "rb").read())
+    return h.hexdigest()[:12]
+
+
 def build(defines=(), out=None):
-    """g++ -> tests/simt/_build/libbpp_emul*.so (git-ignored).  `defines` selects kernel build variants like build.py."""
-    out = out or _OUT
-    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in _DEPS):
+    """g++ -> tests/simt/_build/libbpp_emul_<variant>_<digest>.so (git-ignored).  `defines` selects kernel build switches
+    like build.py -D...; the digest of the sources is part of the file name, so a stale build can never be picked up."""
+    tag = "_".join(d.replace("=", "").replace("BPP_", "").lower() for d in defines) or "default"
+    out = out or os.path.join(_HERE, "_build", "libbpp_emul_%s_%s.so" % (tag[:80], _source_digest(defines)))
+    if os.path.exists(out):
         return out
     os.makedirs(os.path.dirname(out), exist_ok=True)
+    for old in os.listdir(os.path.dirname(out)):              # earlier builds of this variant
+        if old.startswith("libbpp_emul_%s_" % tag[:80]) and old.endswith(".so"):
+            os.remove(os.path.join(os.path.dirname(out), old))
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-I", _HERE] + ["-D" + d for d in defines] + \
-          ["-o", out, os.path.join(_HERE, "emul_kernels.cpp")]
+          ["-o", out + ".tmp", os.path.join(_HERE, "emul_kernels.cpp")]
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
     subprocess.check_call(cmd, env=env)
+    os.replace(out + ".tmp", out)
     return out
 
 
@@ -52,9 +66,7 @@ _libs = {}
 def lib(defines=()):
     key = tuple(defines)
     if key not in _libs:
-        out = None if not key else os.path.join(_HERE, "_build", "libbpp_emul_%s.so" % "_".join(
-            d.replace("=", "").replace("BPP_", "").lower() for d in key))
-        l = C.CDLL(build(key, out))
+        l = C.CDLL(build(key))
         l.emul_env_call.restype = C.c_int
         l.emul_env_call.argtypes = [C.POINTER(_cabi.Config), C.POINTER(_Buffers), C.POINTER(_IO)] + [C.c_int] * 4
         l.emul_sizes.restype = None
