@@ -242,3 +242,12 @@ def test_lane_schedule_does_not_matter(order, defines):
             run_against_oracle(24, (10, 10, 10), False, 2, dict(gen="cut2"), T=12, seed=25)
     finally:
         emul.set_lane_order(0, defines)
+
+
+def test_rule_v1_instantiations():
+    """Rule v1 (Space.check_box as mask rule) on the compile-time sizes and on a size without 128-bit stores: template
+    instantiations the other cases leave out (gcov over the interpreted build: all 24 step-kernel instantiations run)."""
+    run_against_oracle(96, (10, 10, 10), False, 1, dict(gen="rs"), T=16, seed=41, edge_every=5)
+    run_against_oracle(40, (20, 20, 20), True, 1, dict(gen="rs"), T=12, seed=42, num_sms=4)
+    items = np.array([(1, 2, 1), (3, 3, 2), (6, 2, 1), (2, 8, 3)], dtype=np.uint8)
+    run_against_oracle(50, (7, 9, 6), False, 1, dict(gen="rs", item_set=items), T=16, seed=43, edge_every=4)
