@@ -82,6 +82,8 @@ def lib(defines=()):
         l.emul_import_state.restype = C.c_int
         l.emul_import_state.argtypes = [C.POINTER(_cabi.Config), C.POINTER(_Buffers)] + [C.c_void_p] * 4
         l.emul_collectives.restype = C.c_uint64
+        l.emul_debug_draws.restype = C.c_int
+        l.emul_debug_draws.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]
         l.emul_set_lane_order.restype = None
         l.emul_set_lane_order.argtypes = [C.c_int]
         l.emul_choose_batches.restype = None
@@ -265,3 +267,10 @@ def choose_batches(N, warps, defines=()):
 def set_lane_order(order, defines=()):
     """0: lanes of a warp resume in order 0..31 between collectives, 1: 31..0, 2: odd lanes first."""
     lib(defines).emul_set_lane_order(int(order))
+
+
+def debug_draws(seed, domain, aux, gid, n, defines=()):
+    """bpp_debug_draws_kernel: the first n draws of Philox stream (seed, domain, aux, gid) as the kernels compute them."""
+    out = np.zeros(n, dtype=np.uint32)
+    assert lib(defines).emul_debug_draws(int(seed), int(domain), int(aux), int(gid), int(n), _ptr(out)) == 0
+    return out

@@ -117,6 +117,11 @@ int emul_import_state(const bpp_config *cfg, const EmulBuffers *b, const int32_t
     return launch_import_state(make_params(cfg, b), plain, box, counter, vol, nullptr);
 }
 
+int emul_debug_draws(unsigned long long seed, uint32_t domain, uint32_t aux, unsigned long long gid, int n, uint32_t *out)
+{
+    return launch_debug_draws(seed, domain, aux, gid, n, out, nullptr);
+}
+
 unsigned long long emul_collectives(void) { return simt::M.collectives; }
 void emul_set_lane_order(int order) { simt::g_lane_order = order; }
 

@@ -251,3 +251,12 @@ def test_rule_v1_instantiations():
     run_against_oracle(40, (20, 20, 20), True, 1, dict(gen="rs"), T=12, seed=42, num_sms=4)
     items = np.array([(1, 2, 1), (3, 3, 2), (6, 2, 1), (2, 8, 3)], dtype=np.uint8)
     run_against_oracle(50, (7, 9, 6), False, 1, dict(gen="rs", item_set=items), T=16, seed=43, edge_every=4)
+
+
+def test_philox_streams():
+    """The hand-written Philox4x32-10 of the kernels against the oracle's independent C copy (which tests/test_oracle_golden.py
+    pins to the Random123 known answers); the GPU suite adds cuRAND's own generator."""
+    for seed, dom, aux, gid in [(1234, 0, 0, 0), (1234, 0, 0, 77), (0xDEADBEEFCAFE, 1, 0, 2 ** 33 + 5), (7, 2, 12345, 9)]:
+        got = emul.debug_draws(seed, dom, aux, gid, 70)
+        want = np.array([orc.draw(seed, dom, aux, gid, i) for i in range(70)], dtype=np.uint32)
+        assert np.array_equal(got, want)
