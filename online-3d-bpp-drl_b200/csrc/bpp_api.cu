@@ -202,15 +202,12 @@ int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
         // cutCreator.py:69-76 asserts lo <= dim - lo for every cut (dim > hi), mdCreator.py:73-76 needs a cut that
         // leaves both parts >= lo: both require hi + 1 >= 2 * lo.
         const int axes = cfg->gen_kind == BPP_GEN_CUT1 ? 3 : 1;
-        int lo_min = 255;
         for (int a = 0; a < axes; ++a) {
             if (cfg->lo[a] < 1 || cfg->hi[a] < cfg->lo[a] || cfg->hi[a] > 255 || cfg->hi[a] + 1 < 2 * cfg->lo[a]) {
                 bpp_destroy(e);
                 return fail(BPP_ERR_INVALID, "bpp_create: cut generators need 1 <= lo <= hi and hi + 1 >= 2 * lo per axis");
             }
-            lo_min = cfg->lo[a] < lo_min ? cfg->lo[a] : lo_min;
         }
-        if ((cfg->L + cfg->W + cfg->H) / lo_min > 90) { bpp_destroy(e); return fail(BPP_ERR_INVALID, "bpp_create: bin too deep for the cut generators' split stack"); }
         const long long cap = (long long)(cfg->L / cfg->lo[0]) * (cfg->W / cfg->lo[axes == 3 ? 1 : 0]) * (cfg->H / cfg->lo[axes == 3 ? 2 : 0]);
         if (cap < 1 || cap > 60000) { bpp_destroy(e); return fail(BPP_ERR_INVALID, "bpp_create: episode capacity out of range"); }
         derive_params(*cfg, p);

@@ -50,8 +50,6 @@ struct GenRng {
     }
 };
 
-constexpr int kStack = 96;      // DFS stack of the cut1 split tree; bpp_create checks (L+W+H)/min(lo) <= 90
-
 __device__ __forceinline__ uint32_t pack_item(int x, int y, int z) { return (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)z << 16); }
 
 // list.pop(idx) / list.remove(item at idx) on an array in (shared) memory, by the whole warp
@@ -68,40 +66,68 @@ __device__ __forceinline__ void warp_erase(T *a, int idx, int n, int lane)
     }
 }
 
-// cut1, one warp per episode.  Phase 1 (the split tree) is sequential in the order of the random draws and runs on
-// lane 0; phase 2 (support-ready ordering) uses the warp: lanes test the waiting pieces against the piece just
+// cut1, one warp per episode.  Phase 1, _cut_box (cutCreator.py:79-95), sweeps the piece list level by level, and
+// within one sweep the pieces are independent of each other except for WHICH two draws a piece that must be split
+// consumes (2 per split, in list order) and WHERE its one or two successors land in the next list -- two prefix sums.
+// So a sweep runs with one lane per piece: ballot of the lanes that split, draw index and output slot from the
+// ballots, one Philox evaluation per splitting lane (its two draws share a 4-word block because the index is even).
+// The draws are consumed in exactly the reference's order (tests/test_generator_identity.py).  Pieces are disjoint
+// with every side >= lo, so neither list ever holds more than cap = (L/lo)(W/lo)(H/lo) of them.
+// Phase 2 (support-ready ordering) uses the warp per piece: lanes test the waiting pieces against the piece just
 // emitted, check / raise footprints of the shadow heightmap cell-parallel, and compact the lists with ballots.
 // The lists keep exactly the reference's order (scan order of meta_list, appends to candidates, pop(idx)).
 __device__ int gen_cut1(const EnvParams &p, GenRng &g, uint32_t *out, Piece *leaf, uint16_t *lists, uint8_t *shadow,
-                        Piece *stack, int cap, int lane)
+                        Piece *next, int cap, int lane)
 {
     const int L = p.L, W = p.W, H = p.H;
-    int n_leaf = 0;
-    if (lane == 0) {
-        int sp = 0;
-        stack[sp++] = mk_piece(L, W, H, 0, 0, 0);
-        while (sp > 0) {
-            const Piece b = stack[--sp];
-            const int dim[3] = {px(b), py(b), pz(b)};
-            int bad[3], nbad = 0;
-            for (int a = 0; a < 3; ++a)                                   // _check_box, cutCreator.py:54-58
-                if (dim[a] < p.lo[a] || dim[a] > p.hi[a]) bad[nbad++] = a;
-            if (nbad == 0) { if (n_leaf < cap) leaf[n_leaf++] = b; continue; }
-            const int df = bad[__umulhi(g.next(), (uint32_t)nbad)];          // random.choice, :68
-            const int lo = p.lo[df];
-            int span = dim[df] - 2 * lo + 1;                              // randint(lo, dim - lo), :69-76
-            if (span < 1) span = 1;
-            const int cut = lo + (int)__umulhi(g.next(), (uint32_t)span);
-            Piece p1, p2;                                                 // MetaBox.split, :16-26
-            if (df == 0) { p1 = mk_piece(cut, py(b), pz(b), plx(b), ply(b), plz(b)); p2 = mk_piece(px(b) - cut, py(b), pz(b), plx(b) + cut, ply(b), plz(b)); }
-            else if (df == 1) { p1 = mk_piece(px(b), cut, pz(b), plx(b), ply(b), plz(b)); p2 = mk_piece(px(b), py(b) - cut, pz(b), plx(b), ply(b) + cut, plz(b)); }
-            else { p1 = mk_piece(px(b), py(b), cut, plx(b), ply(b), plz(b)); p2 = mk_piece(px(b), py(b), pz(b) - cut, plx(b), ply(b), plz(b) + cut); }
-            if (sp + 2 <= kStack) { stack[sp++] = p2; stack[sp++] = p1; }  // p1 first => in-order leaves
-        }
-    }
+    const unsigned lt = (1u << lane) - 1u;
+    int n_leaf = 1;
+    if (lane == 0) leaf[0] = mk_piece(L, W, H, 0, 0, 0);
     __syncwarp();
-    n_leaf = __shfl_sync(kFull, n_leaf, 0);
-    g.k = __shfl_sync(kFull, g.k, 0);
+    for (;;) {
+        int n_next = 0;
+        bool again = false;
+        for (int c0 = 0; c0 < n_leaf; c0 += 32) {                         // for box in self.meta_list, :84
+            const int i = c0 + lane;
+            const bool valid = i < n_leaf;
+            const Piece b = valid ? leaf[i] : 0;
+            // _check_box, :54-58: bit a of `bad` = side a lies outside [lo, hi]
+            const unsigned bad = (unsigned)(px(b) < p.lo[0] || px(b) > p.hi[0]) | ((unsigned)(py(b) < p.lo[1] || py(b) > p.hi[1]) << 1) |
+                                 ((unsigned)(pz(b) < p.lo[2] || pz(b) > p.hi[2]) << 2);
+            const bool split = valid && bad != 0u;
+            const unsigned sb = __ballot_sync(kFull, split), vb = __ballot_sync(kFull, valid);
+            const int slot = n_next + __popc(vb & lt) + __popc(sb & lt);
+            if (split) {
+                const uint32_t k = g.k + 2u * (uint32_t)__popc(sb & lt);  // even: both draws come from one block
+                const uint4 blk = philox4x32_10(make_uint4(k >> 2, ((uint32_t)kDomGen << 28) | (g.aux & 0x0FFFFFFFu),
+                                                           (uint32_t)g.gid, (uint32_t)(g.gid >> 32)),
+                                                make_uint2(g.seed_lo, g.seed_hi));
+                const uint32_t u0 = (k & 2u) ? blk.z : blk.x, u1 = (k & 2u) ? blk.w : blk.y;
+                const int r = (int)__umulhi(u0, (uint32_t)__popc(bad));   // random.choice(df_list), :68: the r-th offending axis
+                const unsigned rest = r == 0 ? bad : (r == 1 ? (bad & (bad - 1u)) : 4u);
+                const int df = __ffs(rest) - 1;
+                const int side = df == 0 ? px(b) : (df == 1 ? py(b) : pz(b));
+                const int lo = df == 0 ? p.lo[0] : (df == 1 ? p.lo[1] : p.lo[2]);
+                int span = side - 2 * lo + 1;                             // randint(lo, side - lo), :69-76
+                if (span < 1) span = 1;
+                const int cut = lo + (int)__umulhi(u1, (uint32_t)span);
+                Piece p1, p2;                                             // MetaBox.split, :16-26
+                if (df == 0) { p1 = mk_piece(cut, py(b), pz(b), plx(b), ply(b), plz(b)); p2 = mk_piece(px(b) - cut, py(b), pz(b), plx(b) + cut, ply(b), plz(b)); }
+                else if (df == 1) { p1 = mk_piece(px(b), cut, pz(b), plx(b), ply(b), plz(b)); p2 = mk_piece(px(b), py(b) - cut, pz(b), plx(b), ply(b) + cut, plz(b)); }
+                else { p1 = mk_piece(px(b), py(b), cut, plx(b), ply(b), plz(b)); p2 = mk_piece(px(b), py(b), pz(b) - cut, plx(b), ply(b), plz(b) + cut); }
+                if (slot + 2 <= cap) { next[slot] = p1; next[slot + 1] = p2; }
+            } else if (valid && slot < cap) {
+                next[slot] = b;
+            }
+            n_next += __popc(vb) + __popc(sb);
+            g.k += 2u * (uint32_t)__popc(sb);
+            again = again || sb != 0u;
+        }
+        __syncwarp();
+        Piece *t = leaf; leaf = next; next = t;                           // self.meta_list = copy.deepcopy(new_list), :94
+        n_leaf = min(n_next, cap);
+        if (!again) break;
+    }
     g.blk_idx = 0xffffffffu;
 
     // ordering phase: generate_box_size / _add_candidate / _update, cutCreator.py:98-128
@@ -109,7 +135,6 @@ __device__ int gen_cut1(const EnvParams &p, GenRng &g, uint32_t *out, Piece *lea
     for (int i = lane; i < n_leaf; i += 32) meta[i] = (uint16_t)i;
     for (int k = lane; k < L * W; k += 32) shadow[k] = 0;
     __syncwarp();
-    const unsigned lt = (1u << lane) - 1u;
     int n_meta = n_leaf, n_cand = 0, n_out = 0;
     bool first = true;
     Piece last = 0;
@@ -277,10 +302,10 @@ __global__ void __launch_bounds__(128) bpp_gen_kernel(const EnvParams p, const i
             if (p.gen_kind == 2) {
                 Piece *leaf = reinterpret_cast<Piece *>(scratch);
                 const size_t o1 = ((size_t)p.ep_cap * sizeof(Piece) + 15) & ~(size_t)15;
-                const size_t o2 = o1 + (((size_t)p.ep_cap * 4 + 15) & ~(size_t)15);
-                const size_t o3 = o2 + 1024;
-                n = gen_cut1(p, g, out, leaf, reinterpret_cast<uint16_t *>(scratch + o1), scratch + o2,
-                             reinterpret_cast<Piece *>(scratch + o3), p.ep_cap, lane);
+                const size_t o2 = 2 * o1;
+                const size_t o3 = o2 + (((size_t)p.ep_cap * 4 + 15) & ~(size_t)15);
+                n = gen_cut1(p, g, out, leaf, reinterpret_cast<uint16_t *>(scratch + o2), scratch + o3,
+                             reinterpret_cast<Piece *>(scratch + o1), p.ep_cap, lane);
             } else {
                 Piece *inv = reinterpret_cast<Piece *>(scratch);
                 Piece *val = inv + p.ep_cap + 64;
@@ -311,9 +336,8 @@ cudaError_t launch_gen(const EnvParams &p, int mode, uint32_t e0, int num_sms, c
 
 size_t gen_scratch_bytes_per_bin(int gen_kind, int cap)
 {
-    if (gen_kind == 2)      // leaf pieces | meta + candidate lists | shadow heightmap (<= 1024) | split stack
-        return (((size_t)cap * sizeof(Piece) + 15) & ~(size_t)15) + (((size_t)cap * 4 + 15) & ~(size_t)15) + 1024 +
-               (((size_t)kStack * sizeof(Piece) + 15) & ~(size_t)15);
+    if (gen_kind == 2)      // piece list | piece list of the next sweep | meta + candidate lists | shadow heightmap (<= 1024)
+        return 2 * (((size_t)cap * sizeof(Piece) + 15) & ~(size_t)15) + (((size_t)cap * 4 + 15) & ~(size_t)15) + 1024;
     return (((size_t)(cap + 64) * 2 * sizeof(Piece)) + 15) & ~(size_t)15;
 }
 

@@ -156,38 +156,47 @@ typedef struct { uint64_t seed, gid; uint32_t aux, k; } gen_rng;
 static inline uint32_t gen_next(gen_rng *g) { return orc_draw(g->seed, DOM_GEN, g->aux, g->gid, g->k++); }
 
 /* envs/bpp0/cutCreator.py:32-128.
- * _cut_box (:79-95) sweeps a list replacing each out-of-range piece by its two halves in place;
- * the resulting leaf order is the in-order leaf sequence of the split tree, which the explicit
- * stack below reproduces.  Then generate_box_size (:112-128) pops a uniformly random ready piece
- * (_add_candidate :98-107) until none is left.  The emission order does not depend on the agent,
- * so the whole episode is produced at reset. */
+ * _cut_box (:79-95) sweeps the piece list level by level: every out-of-range piece of the current
+ * list is replaced by its two halves (random.choice of the offending axis :68, random.randint of
+ * the cut :76), in list order, until a sweep splits nothing.  The draws are consumed in exactly
+ * that order (tests/test_generator_identity.py feeds the same stream to the unmodified reference).
+ * Then generate_box_size (:112-128) pops a uniformly random ready piece (_add_candidate :98-107)
+ * until none is left.  The emission order does not depend on the agent, so the whole episode is
+ * produced at reset. */
 int32_t orc_gen_cut1(const orc_config *cfg, uint64_t gid, uint32_t episode,
                      uint8_t *items, uint8_t *pos, int32_t cap)
 {
     const int32_t L = cfg->L, W = cfg->W, H = cfg->H;
     gen_rng g = { cfg->seed, gid, episode, 0 };
-    piece_t *leaf = (piece_t *)malloc(sizeof(piece_t) * (size_t)(cap + 1));
-    piece_t *stack = (piece_t *)malloc(sizeof(piece_t) * (size_t)(cap + 64));
-    int32_t n_leaf = 0, sp = 0;
-    stack[sp++] = (piece_t){ L, W, H, 0, 0, 0 };
-    while (sp > 0) {
-        piece_t b = stack[--sp];
-        int32_t dim[3] = { b.x, b.y, b.z };
-        int32_t bad[3], nbad = 0;
-        for (int32_t a = 0; a < 3; ++a)                 /* _check_box, cutCreator.py:54-58 */
-            if (dim[a] < cfg->lo[a] || dim[a] > cfg->hi[a]) bad[nbad++] = a;
-        if (nbad == 0) { if (n_leaf < cap) leaf[n_leaf++] = b; continue; }
-        int32_t df = bad[mulhi32(gen_next(&g), (uint32_t)nbad)];        /* :68 */
-        int32_t lo = cfg->lo[df];
-        int32_t span = dim[df] - 2 * lo + 1;            /* randint(lo, dim-lo), :69-76 */
-        if (span < 1) span = 1;                         /* reference asserts; unreachable for valid configs */
-        int32_t cut = lo + (int32_t)mulhi32(gen_next(&g), (uint32_t)span);
-        piece_t p1 = b, p2 = b;                         /* MetaBox.split, :16-26 */
-        if (df == 0) { p1.x = cut; p2.x = b.x - cut; p2.lx = b.lx + cut; }
-        else if (df == 1) { p1.y = cut; p2.y = b.y - cut; p2.ly = b.ly + cut; }
-        else { p1.z = cut; p2.z = b.z - cut; p2.lz = b.lz + cut; }
-        stack[sp++] = p2;                               /* p1 is expanded first => in-order leaves */
-        stack[sp++] = p1;
+    /* pieces are disjoint with every side >= lo, so a list never holds more than cap of them */
+    piece_t *leaf = (piece_t *)malloc(sizeof(piece_t) * (size_t)(cap + 2));
+    piece_t *next = (piece_t *)malloc(sizeof(piece_t) * (size_t)(cap + 2));
+    int32_t n_leaf = 1;
+    leaf[0] = (piece_t){ L, W, H, 0, 0, 0 };
+    for (int again = 1; again;) {
+        again = 0;
+        int32_t n_next = 0;
+        for (int32_t i = 0; i < n_leaf; ++i) {          /* for box in self.meta_list, :84 */
+            piece_t b = leaf[i];
+            int32_t dim[3] = { b.x, b.y, b.z };
+            int32_t bad[3], nbad = 0;
+            for (int32_t a = 0; a < 3; ++a)             /* _check_box, cutCreator.py:54-58 */
+                if (dim[a] < cfg->lo[a] || dim[a] > cfg->hi[a]) bad[nbad++] = a;
+            if (nbad == 0) { if (n_next < cap) next[n_next++] = b; continue; }
+            int32_t df = bad[mulhi32(gen_next(&g), (uint32_t)nbad)];        /* :68 */
+            int32_t lo = cfg->lo[df];
+            int32_t span = dim[df] - 2 * lo + 1;        /* randint(lo, dim-lo), :69-76 */
+            if (span < 1) span = 1;                     /* reference asserts; unreachable for valid configs */
+            int32_t cut = lo + (int32_t)mulhi32(gen_next(&g), (uint32_t)span);
+            piece_t p1 = b, p2 = b;                     /* MetaBox.split, :16-26 */
+            if (df == 0) { p1.x = cut; p2.x = b.x - cut; p2.lx = b.lx + cut; }
+            else if (df == 1) { p1.y = cut; p2.y = b.y - cut; p2.ly = b.ly + cut; }
+            else { p1.z = cut; p2.z = b.z - cut; p2.lz = b.lz + cut; }
+            if (n_next + 2 <= cap) { next[n_next++] = p1; next[n_next++] = p2; }
+            again = 1;
+        }
+        piece_t *t = leaf; leaf = next; next = t;       /* self.meta_list = copy.deepcopy(new_list), :94 */
+        n_leaf = n_next;
     }
     /* ordering phase */
     int32_t *shadow = (int32_t *)calloc((size_t)(L * W), sizeof(int32_t));
@@ -227,7 +236,7 @@ int32_t orc_gen_cut1(const orc_config *cfg, uint64_t gid, uint32_t episode,
         for (int32_t r = 0; r < p.x; ++r)               /* _update, :109-110 */
             for (int32_t c = 0; c < p.y; ++c) shadow[(p.lx + r) * W + p.ly + c] += p.z;
     }
-    free(leaf); free(stack); free(shadow); free(meta); free(cand);
+    free(leaf); free(next); free(shadow); free(meta); free(cand);
     return n_out;
 }
 

@@ -2,7 +2,8 @@
 RandomBoxCreator) against invariants and against statistics recorded from the reference's own
 (MT19937-driven) generators and datasets (tests/golden/gen_stats.npz, datasets.npz).
 
-Bit-level parity is impossible by construction (different RNG); these tests pin the *distribution*."""
+The reference's own MT19937 streams cannot be reproduced, so these tests pin the *distribution*; the algorithm itself
+is pinned episode for episode in tests/test_generator_identity.py (reference generators fed with the Philox stream)."""
 import os
 
 import numpy as np

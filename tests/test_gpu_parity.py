@@ -514,3 +514,12 @@ def test_step_host_pageable_buffers(env_mod, n):
         assert np.array_equal(t2n(a.reward_t), rew) and np.array_equal(t2n(a.done_t), done)
         assert np.array_equal(t2n(a.counter_t), cnt) and np.array_equal(t2n(a.ratio_t), rat)
     assert a.metrics() == b.metrics()
+
+
+@pytest.mark.parametrize("rot", [False, True])
+@pytest.mark.parametrize("variant", [2, 1])
+def test_headline_shape_every_bin_vs_oracle(env_mod, rot, variant):
+    """The workload bench.py times (2^19 bins, 10x10x10, rs; kernel instantiation <ROT, VARIANT, true, 10, true> with
+    32-bin warp batches): every bin against the oracle at every step, rotation off and on, mask rules v2 and v1."""
+    m = run_against_oracle(env_mod, 1 << 19, (10, 10, 10), rot, variant, dict(data_type="rs"), T=6, seed=1234, edge_every=3)
+    assert m["steps"] == 6 << 19
