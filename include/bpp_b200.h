@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BPP_ABI_VERSION 1
+#define BPP_ABI_VERSION 2
 
 typedef enum {
     BPP_OK = 0,
@@ -109,6 +109,43 @@ int32_t bpp_step_host(bpp_env *env, const int64_t *actions_host, float *obs, flo
                       float *reward_host, uint8_t *done_host, int32_t *counter_host,
                       float *ratio_host, int64_t *sample, void *stream);
 
+/* -- step with packed results.  What VecPyTorch.step_wait hands back per env (acktr/envs.py:189-193: reward, and through
+ *    infos the counter / ratio of bin3D.py:111,123-125) travels as ONE 16-byte record per bin, written with a single
+ *    128-bit store (or one PCIe write when `results` is pinned host memory):
+ *      reward       10 * item volume / (L*W*H) of the step, 0 when the episode ended   (bin3D.py:121)
+ *      vol          placed volume after the step; ratio = vol / (L*W*H) and Monitor's episode return r = 10 * vol / (L*W*H)
+ *                   follow exactly on the host (space.py:146-151, baselines/bench/monitor.py:64)
+ *      counter      len(space.boxes) after the step (info['counter'])
+ *      next_action  a uniformly random valid action for the state after the step (policy stand-in; ignore otherwise)
+ *    `done` stays a separate byte array so that the host can take it as np.bool_[N] without a pass over the records.
+ *    n_steps >= 1 env steps run in ONE launch: step 1 takes `actions`, every later step the action the previous one
+ *    sampled (policy-free rollouts on small envs, where a launch per step costs more than the step); rs / replay
+ *    generators only.  results / done describe the LAST step; the episode metrics count all of them.
+ *    `sample` (int64[N], may be NULL) receives next_action as well, for callers that feed it back as `actions`. */
+typedef struct {
+    float reward;
+    int32_t vol;
+    int32_t counter;
+    int32_t next_action;
+} bpp_result;
+
+int32_t bpp_step_packed(bpp_env *env, const int64_t *actions, float *obs, float *mask, bpp_result *results,
+                        uint8_t *done, int64_t *sample, int32_t n_steps, void *stream);
+
+/* Same with HOST results / done (pinned and mapped, e.g. from bpp_host_alloc: the kernel writes them in place over
+ * PCIe; ordinary memory is staged through device copies).  actions_host may be pinned host memory (read in place),
+ * ordinary host memory (staged) or a device pointer (a policy that lives on the GPU).  `sample` (device, may be NULL)
+ * receives the next sampled action as int64 as well.  One step; synchronises `stream`. */
+int32_t bpp_step_packed_host(bpp_env *env, const int64_t *actions_host, float *obs, float *mask,
+                             bpp_result *results_host, uint8_t *done_host, int64_t *sample, void *stream);
+
+/* -- pinned, device-mapped host memory placed on the NUMA node of `device` (the calling thread is bound to that node's
+ *    CPUs while the pages are allocated and touched, then gets its affinity back), and a helper that binds the calling
+ *    thread there for good -- what a per-GPU rollout worker should do before it starts launching. */
+int32_t bpp_host_alloc(int32_t device, uint64_t bytes, void **out);
+int32_t bpp_host_free(void *ptr);
+int32_t bpp_bind_thread_to_device(int32_t device);
+
 /* -- stateless mask: acktr/utils.py:37-62 get_possible_position / :64-94 get_rotation_mask on a batch
  *    of observations (float32[n][4LW], as delivered by VecPyTorch), and the same on raw state
  *    (plain int32[n][LW] = Space.plain, box int32[n][3]).  mask float32[n][LW(1+rot)]. */
@@ -123,7 +160,8 @@ int32_t bpp_check_box(const int32_t *plain, const int32_t *query, int32_t n, int
                       int32_t H, int32_t variant, int32_t *out, void *stream);
 
 /* -- state in reference dtypes (Space.plain int32[N][LW], next box int32[N][3], len(space.boxes)
- *    int32[N], placed volume int32[N]); NULL pointers are skipped.  import marks the env as reset. */
+ *    int32[N], placed volume int32[N]); NULL pointers are skipped.  import needs an env that has been reset (the item
+ *    generators' per-bin state comes from there) and heights within [0, H], else BPP_ERR_STATE / BPP_ERR_INVALID. */
 int32_t bpp_export_state(bpp_env *env, int32_t *plain, int32_t *box, int32_t *counter, int32_t *vol,
                          void *stream);
 int32_t bpp_import_state(bpp_env *env, const int32_t *plain, const int32_t *box, const int32_t *counter,

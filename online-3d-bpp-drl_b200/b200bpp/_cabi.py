@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # BPP_B200_LIB lets kernel experiments A/B a differently built library; the default is the in-tree build
 LIB_PATH = os.environ.get("BPP_B200_LIB") or os.path.join(_HERE, "libbpp_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 GEN_RS, GEN_REPLAY, GEN_CUT1, GEN_CUT2 = 0, 1, 2, 3
 GEN_KINDS = {"rs": GEN_RS, "replay": GEN_REPLAY, "cut1": GEN_CUT1, "cut2": GEN_CUT2}
 MASK_V1, MASK_V2 = 1, 2
@@ -47,6 +47,11 @@ SYMBOLS = {
     "bpp_reset": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "bpp_step": (_i32, [_vp] * 10),
     "bpp_step_host": (_i32, [_vp] * 10),
+    "bpp_step_packed": (_i32, [_vp] * 7 + [_i32, _vp]),
+    "bpp_step_packed_host": (_i32, [_vp] * 8),
+    "bpp_host_alloc": (_i32, [_i32, C.c_uint64, C.POINTER(_vp)]),
+    "bpp_host_free": (_i32, [_vp]),
+    "bpp_bind_thread_to_device": (_i32, [_i32]),
     "bpp_mask_from_obs": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "bpp_mask_from_plain": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "bpp_check_box": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),

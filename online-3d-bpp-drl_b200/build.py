@@ -18,19 +18,14 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 # Named kernel build variants (switches in csrc/bpp_common.cuh): tools/ab_bench.py times them against the default build on a B200;
 # tests/test_kernel_emul.py checks them bit for bit on the CPU.  Built next to the default as b200bpp/variants/*.so.
 VARIANTS = {
-    # every switch off: the kernel as it stood before the packed sweep / lane check / square copy / plain stores
-    "baseline": ["BPP_PACKED_SWEEP=0", "BPP_LANE_CHECK=0", "BPP_SQUARE_COPY=0", "BPP_PLAIN_STORES=0"],
-    "packed": ["BPP_PACKED_SWEEP=1", "BPP_LANE_CHECK=0", "BPP_SQUARE_COPY=0", "BPP_PLAIN_STORES=0"],
-    "streaming": ["BPP_PLAIN_STORES=0"],          # the default build with streaming (evict-first) output stores
-    # candidates that cut load/store-unit work (bit-exact under tests/test_kernel_emul.py, not yet timed):
-    "split": ["BPP_PAIRS_SPLIT=1"],               # bank-conflict-free layout of the packed sweep's pairs
-    "nolut": ["BPP_PLANE_LUT=0"],                 # observation planes converted in registers instead of 3 LDS.128
-    "words": ["BPP_LANE_CHECK_WORDS=1"],          # lane-per-bin check: 2 aligned word loads per row instead of 5 bytes
-    "lsu": ["BPP_PAIRS_SPLIT=1", "BPP_PLANE_LUT=0", "BPP_LANE_CHECK_WORDS=1"],
-    "tier": ["BPP_TWO_TIER=1"],                   # whole rounds of large batches, then one round of small ones
-    "all": ["BPP_PAIRS_SPLIT=1", "BPP_PLANE_LUT=0", "BPP_LANE_CHECK_WORDS=1", "BPP_TWO_TIER=1"],
-    "occ5": ["BPP_MIN_BLOCKS=5"],                 # 48 registers, 40 warps per SM (spills ~110 B per thread: re-measure)
-    "split_occ5": ["BPP_PAIRS_SPLIT=1", "BPP_MIN_BLOCKS=5"],
+    # round-1 kernel switches all off (the timing baseline of round 1) and the ordinary LDG/STG path of this round
+    "baseline": ["BPP_PACKED_SWEEP=0", "BPP_LANE_CHECK=0", "BPP_SQUARE_COPY=0", "BPP_PLAIN_STORES=0", "BPP_TMA=0", "BPP_UNIFORM=0"],
+    "notma": ["BPP_TMA=0"],
+    "nouni": ["BPP_UNIFORM=0"],                   # ordinary instantiations without the uniform-datapath trick
+    # bulk-copy path: bins per warp batch x resident CTAs per SM
+    "n16x5": ["BPP_TMA_BPW_LOG2=4", "BPP_TMA_MIN_BLOCKS=5"],
+    "rot5": ["BPP_TMA_MIN_BLOCKS_ROT=5"],
+    "rot32": ["BPP_TMA_BPW_LOG2_ROT=5", "BPP_TMA_MIN_BLOCKS_ROT=3"],
 }
 
 

@@ -2,7 +2,10 @@
 // validation, device memory owned by the env, launches.  No CPU fallback exists: without a usable
 // sm_100 device every entry point fails with BPP_ERR_NO_DEVICE / BPP_ERR_CUDA.
 #include <atomic>
+#include <cctype>
 #include <cstdio>
+#include <cstdlib>
+#include <sched.h>
 #include <cstring>
 #include <new>
 #include <string>
@@ -46,12 +49,14 @@ int device_grid_cap(int device, int *num_sms)
     return BPP_OK;
 }
 
-// Device-side alias of a pinned (page-locked, mapped) host buffer, or nullptr for pageable memory.
-inline void *mapped_alias(void *host_ptr)
+// Device-side alias of a pinned (page-locked, mapped) host buffer -- or the pointer itself when it already is device
+// (or managed) memory --, nullptr for pageable host memory.
+inline void *mapped_alias(void *ptr)
 {
-    if (!host_ptr) return nullptr;
+    if (!ptr) return nullptr;
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, host_ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return ptr;
     if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
     return at.devicePointer;
 }
@@ -63,7 +68,6 @@ struct bpp_env {
     EnvParams p;
     int rot, variant;
     int num_sms;
-    size_t smem;
     bool was_reset;
     unsigned long long steps;
     // device memory owned by the env
@@ -83,10 +87,15 @@ struct bpp_env {
     // worker streams / events for the chunk-pipelined host entry point
     cudaStream_t ws[2];
     cudaEvent_t ev_start, ev_done[2];
-    // last host buffers seen by bpp_step_host and their device aliases (pointer attribute queries are slow)
+    // last host buffers seen by the host entry points and their device aliases (pointer attribute queries are slow);
+    // re-validated every kZcRecheck calls: a caller may have freed a pinned buffer and passed ordinary memory at
+    // the same address
     const void *zc_host[5];
     void *zc_dev[5];
     bool zc_valid, zc_ok;
+    unsigned zc_age;
+    bpp_result *d_results;      // staging of the packed host entry point (pageable buffers)
+    int32_t *d_flag;            // import-state validation
 };
 
 extern "C" {
@@ -100,7 +109,8 @@ uint64_t bpp_launch_count(void) { return g_launches.load(); }
 const char *bpp_build_info(void)
 {
     return "packed_sweep=" BPP_STR(BPP_PACKED_SWEEP) " lane_check=" BPP_STR(BPP_LANE_CHECK) " square_copy=" BPP_STR(BPP_SQUARE_COPY)
-           " plain_stores=" BPP_STR(BPP_PLAIN_STORES) " pairs_split=" BPP_STR(BPP_PAIRS_SPLIT)
+           " plain_stores=" BPP_STR(BPP_PLAIN_STORES) " pairs_split=" BPP_STR(BPP_PAIRS_SPLIT) " tma=" BPP_STR(BPP_TMA)
+           " tma_bpw_log2=" BPP_STR(BPP_TMA_BPW_LOG2) "/" BPP_STR(BPP_TMA_BPW_LOG2_ROT)
            " warps_per_block=" BPP_STR(BPP_WARPS_PER_BLOCK) " sm_100a";
 }
 
@@ -112,6 +122,7 @@ int32_t bpp_destroy(bpp_env *env)
     cudaFree(env->d_ep_items); cudaFree(env->d_ep_len2); cudaFree(env->d_gen_list); cudaFree(env->d_gen_count); cudaFree(env->d_gen_scratch);
     cudaFree(env->d_traj_len); cudaFree(env->d_metrics); cudaFree(env->d_actions);
     cudaFree(env->d_reward); cudaFree(env->d_ratio); cudaFree(env->d_done); cudaFree(env->d_counter);
+    cudaFree(env->d_results); cudaFree(env->d_flag);
     for (int k = 0; k < 2; ++k) {
         if (env->ws[k]) cudaStreamDestroy(env->ws[k]);
         if (env->ev_done[k]) cudaEventDestroy(env->ev_done[k]);
@@ -240,6 +251,8 @@ int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
     BPP_CREATE_CUDA(cudaMalloc(&e->d_ratio, N * sizeof(float)));
     BPP_CREATE_CUDA(cudaMalloc(&e->d_done, N));
     BPP_CREATE_CUDA(cudaMalloc(&e->d_counter, N * sizeof(int32_t)));
+    BPP_CREATE_CUDA(cudaMalloc(&e->d_flag, sizeof(int32_t)));
+    BPP_CREATE_CUDA(cudaMemset(e->d_flag, 0, sizeof(int32_t)));
     p.hm = e->d_hm; p.sc = e->d_sc; p.metrics = e->d_metrics;
 
     for (int k = 0; k < 2; ++k) {
@@ -247,7 +260,6 @@ int32_t bpp_create(const bpp_config *cfg, bpp_env **out)
         BPP_CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming));
     }
     BPP_CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming));
-    e->smem = step_smem_bytes(p);
     *out = e;
     return BPP_OK;
 }
@@ -270,8 +282,9 @@ static int run_step_range(bpp_env *env, const StepIO &io_all, int mode, long lon
     if (io.counter) io.counter += b0;
     if (io.ratio) io.ratio += b0;
     if (io.sample) io.sample += b0;
+    if (io.packed) io.packed += b0;
     const bool vec4 = (p.A % 4 == 0) && (!io.obs || aligned16(io.obs)) && (!io.mask || aligned16(io.mask));
-    BPP_CUDA(launch_step(p, io, mode, env->rot, env->variant, vec4, env->num_sms, env->smem, st));
+    BPP_CUDA(launch_step(p, io, mode, env->rot, env->variant, vec4, env->num_sms, st));
     g_launches.fetch_add(1);
     return BPP_OK;
 }
@@ -327,6 +340,25 @@ int32_t bpp_step(bpp_env *env, const int64_t *actions, float *obs, float *mask, 
     return BPP_OK;
 }
 
+
+// Device aliases of up to five host buffers (null entries allowed): true when every non-null one is pinned and mapped.
+// The answer is cached per env, keyed on the pointer values, and re-validated every kZcRecheck calls.
+constexpr unsigned kZcRecheck = 256;
+static bool zero_copy_aliases(bpp_env *env, const void *const hosts[5])
+{
+    if (!env->zc_valid || std::memcmp(hosts, env->zc_host, 5 * sizeof(void *)) != 0 || ++env->zc_age >= kZcRecheck) {
+        std::memcpy(env->zc_host, hosts, 5 * sizeof(void *));
+        env->zc_ok = true;
+        for (int k = 0; k < 5; ++k) {
+            env->zc_dev[k] = hosts[k] ? mapped_alias(const_cast<void *>(hosts[k])) : nullptr;
+            if (hosts[k] && !env->zc_dev[k]) env->zc_ok = false;
+        }
+        env->zc_valid = true;
+        env->zc_age = 0;
+    }
+    return env->zc_ok;
+}
+
 int32_t bpp_step_host(bpp_env *env, const int64_t *actions_host, float *obs, float *mask, float *reward_host,
                       uint8_t *done_host, int32_t *counter_host, float *ratio_host, int64_t *sample, void *stream)
 {
@@ -348,16 +380,7 @@ int32_t bpp_step_host(bpp_env *env, const int64_t *actions_host, float *obs, flo
     // phases), so the transfers overlap the tile work of other warps and no staging copy is needed.
     {
         const void *hosts[5] = {actions_host, reward_host, ratio_host, done_host, counter_host};
-        if (!env->zc_valid || std::memcmp(hosts, env->zc_host, sizeof(hosts)) != 0) {
-            std::memcpy(env->zc_host, hosts, sizeof(hosts));
-            env->zc_ok = true;
-            for (int k = 0; k < 5; ++k) {
-                env->zc_dev[k] = hosts[k] ? mapped_alias(const_cast<void *>(hosts[k])) : nullptr;
-                if (hosts[k] && !env->zc_dev[k]) env->zc_ok = false;
-            }
-            env->zc_valid = true;
-        }
-        if (env->zc_ok) {
+        if (zero_copy_aliases(env, hosts)) {
             StepIO z = io;
             z.actions = static_cast<const long long *>(env->zc_dev[0]);
             z.reward = static_cast<float *>(env->zc_dev[1]);
@@ -402,6 +425,140 @@ int32_t bpp_step_host(bpp_env *env, const int64_t *actions_host, float *obs, flo
     }
     env->steps += (unsigned long long)N;
     BPP_CUDA(cudaStreamSynchronize(st));
+    return BPP_OK;
+}
+
+
+int32_t bpp_step_packed(bpp_env *env, const int64_t *actions, float *obs, float *mask, bpp_result *results,
+                        uint8_t *done, int64_t *sample, int32_t n_steps, void *stream)
+{
+    if (int rc = enter(env, "bpp_step_packed")) return rc;
+    if (!env->was_reset) return fail(BPP_ERR_STATE, "bpp_step_packed: call bpp_reset first");
+    if (!actions || !results || !done || !obs || !mask) return fail(BPP_ERR_INVALID, "bpp_step_packed: null pointer");
+    if (!aligned16(results)) return fail(BPP_ERR_INVALID, "bpp_step_packed: results must be 16-byte aligned");
+    if (n_steps < 1) return fail(BPP_ERR_INVALID, "bpp_step_packed: n_steps must be >= 1");
+    if (n_steps > 1 && env->p.gen_kind >= 2)
+        return fail(BPP_ERR_INVALID, "bpp_step_packed: several steps per launch need the rs or replay generator "
+                                     "(cut1 / cut2 refill their episode buffers between steps)");
+    StepIO io{};
+    io.actions = reinterpret_cast<const long long *>(actions);
+    io.obs = obs; io.mask = mask; io.done = done;
+    io.packed = reinterpret_cast<uint4 *>(results);
+    io.sample = reinterpret_cast<long long *>(sample);
+    io.n_steps = n_steps;
+    if (int rc = run_step(env, io, kModeStep, stream)) return rc;
+    if (env->p.gen_kind >= 2) {
+        BPP_CUDA(launch_gen(env->p, 1, 0u, env->num_sms, as_stream(stream)));
+        g_launches.fetch_add(1);
+    }
+    env->steps += (unsigned long long)env->p.N * (unsigned long long)n_steps;
+    return BPP_OK;
+}
+
+int32_t bpp_step_packed_host(bpp_env *env, const int64_t *actions_host, float *obs, float *mask,
+                             bpp_result *results_host, uint8_t *done_host, int64_t *sample, void *stream)
+{
+    if (int rc = enter(env, "bpp_step_packed_host")) return rc;
+    if (!env->was_reset) return fail(BPP_ERR_STATE, "bpp_step_packed_host: call bpp_reset first");
+    if (!actions_host || !results_host || !done_host || !obs || !mask)
+        return fail(BPP_ERR_INVALID, "bpp_step_packed_host: null pointer");
+    cudaStream_t st = as_stream(stream);
+    const size_t N = (size_t)env->p.N;
+    StepIO io{};
+    io.obs = obs; io.mask = mask; io.n_steps = 1;
+    io.sample = reinterpret_cast<long long *>(sample);
+    const void *hosts[5] = {actions_host, results_host, nullptr, done_host, nullptr};
+    const bool zc = zero_copy_aliases(env, hosts) && aligned16(env->zc_dev[1]);
+    if (zc) {       // the kernel reads the actions and writes one 16-byte record + one done byte per bin over PCIe
+        io.actions = static_cast<const long long *>(env->zc_dev[0]);
+        io.packed = static_cast<uint4 *>(env->zc_dev[1]);
+        io.done = static_cast<uint8_t *>(env->zc_dev[3]);
+    } else {        // ordinary host memory: staged through device buffers
+        if (!env->d_results) BPP_CUDA(cudaMalloc(&env->d_results, N * sizeof(bpp_result)));
+        BPP_CUDA(cudaMemcpyAsync(env->d_actions, actions_host, N * sizeof(long long), cudaMemcpyHostToDevice, st));
+        io.actions = env->d_actions;
+        io.packed = reinterpret_cast<uint4 *>(env->d_results);
+        io.done = env->d_done;
+    }
+    if (int rc = run_step(env, io, kModeStep, stream)) return rc;
+    if (env->p.gen_kind >= 2) {
+        BPP_CUDA(launch_gen(env->p, 1, 0u, env->num_sms, st));
+        g_launches.fetch_add(1);
+    }
+    if (!zc) {
+        BPP_CUDA(cudaMemcpyAsync(results_host, env->d_results, N * sizeof(bpp_result), cudaMemcpyDeviceToHost, st));
+        BPP_CUDA(cudaMemcpyAsync(done_host, env->d_done, N, cudaMemcpyDeviceToHost, st));
+    }
+    env->steps += (unsigned long long)N;
+    BPP_CUDA(cudaStreamSynchronize(st));
+    return BPP_OK;
+}
+
+// CPUs of the NUMA node a device hangs off: /sys/bus/pci/devices/<bdf>/local_cpulist ("0-31,64-95")
+static bool device_local_cpus(int device, cpu_set_t *set)
+{
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), device) != cudaSuccess) { cudaGetLastError(); return false; }
+    for (char *c = bdf; *c; ++c) *c = (char)std::tolower((unsigned char)*c);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bdf + "/local_cpulist";
+    FILE *f = std::fopen(path.c_str(), "r");
+    if (!f) return false;
+    char buf[4096] = {0};
+    const size_t n = std::fread(buf, 1, sizeof(buf) - 1, f);
+    std::fclose(f);
+    if (n == 0) return false;
+    CPU_ZERO(set);
+    int count = 0;
+    for (char *q = buf; *q && *q != '\n';) {
+        char *e = nullptr;
+        const long a = std::strtol(q, &e, 10);
+        if (e == q) break;
+        long b = a;
+        if (*e == '-') { q = e + 1; b = std::strtol(q, &e, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET((int)c, set); ++count; }
+        q = (*e == ',') ? e + 1 : e;
+        if (*e != ',') break;
+    }
+    return count > 0;
+}
+
+int32_t bpp_bind_thread_to_device(int32_t device)
+{
+    cpu_set_t local, allowed, both;
+    if (!device_local_cpus(device, &local)) return fail(BPP_ERR_INVALID, "bpp_bind_thread_to_device: no local_cpulist for this device");
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return fail(BPP_ERR_INVALID, "bpp_bind_thread_to_device: sched_getaffinity failed");
+    CPU_AND(&both, &local, &allowed);
+    if (CPU_COUNT(&both) == 0) return fail(BPP_ERR_INVALID, "bpp_bind_thread_to_device: none of the device-local CPUs is allowed here");
+    if (sched_setaffinity(0, sizeof(both), &both) != 0) return fail(BPP_ERR_INVALID, "bpp_bind_thread_to_device: sched_setaffinity failed");
+    return BPP_OK;
+}
+
+int32_t bpp_host_alloc(int32_t device, uint64_t bytes, void **out)
+{
+    if (!out || bytes == 0) return fail(BPP_ERR_INVALID, "bpp_host_alloc: bad arguments");
+    *out = nullptr;
+    BPP_CUDA(cudaSetDevice(device));
+    // first touch decides the NUMA node of the pages: do it from a CPU next to the device, then restore the affinity
+    cpu_set_t saved, local, both;
+    const bool have_saved = sched_getaffinity(0, sizeof(saved), &saved) == 0;
+    bool bound = false;
+    if (have_saved && device_local_cpus(device, &local)) {
+        CPU_AND(&both, &local, &saved);
+        if (CPU_COUNT(&both) > 0) bound = sched_setaffinity(0, sizeof(both), &both) == 0;
+    }
+    void *ptr = nullptr;
+    const cudaError_t e = cudaHostAlloc(&ptr, (size_t)bytes, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e == cudaSuccess) std::memset(ptr, 0, (size_t)bytes);
+    if (bound) sched_setaffinity(0, sizeof(saved), &saved);
+    if (e != cudaSuccess) return fail(BPP_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    *out = ptr;
+    return BPP_OK;
+}
+
+int32_t bpp_host_free(void *ptr)
+{
+    if (!ptr) return BPP_OK;
+    BPP_CUDA(cudaFreeHost(ptr));
     return BPP_OK;
 }
 
@@ -485,9 +642,16 @@ int32_t bpp_import_state(bpp_env *env, const int32_t *plain, const int32_t *box,
                          const int32_t *vol, void *stream)
 {
     if (int rc = enter(env, "bpp_import_state")) return rc;
-    BPP_CUDA(launch_import_state(env->p, plain, box, counter, vol, as_stream(stream)));
+    // the per-bin generator state (Philox counters, replay row, pre-cut episodes) only exists after a reset
+    if (!env->was_reset) return fail(BPP_ERR_STATE, "bpp_import_state: call bpp_reset first");
+    cudaStream_t st = as_stream(stream);
+    BPP_CUDA(cudaMemsetAsync(env->d_flag, 0, sizeof(int32_t), st));
+    BPP_CUDA(launch_import_state(env->p, plain, box, counter, vol, env->d_flag, st));
     g_launches.fetch_add(1);
-    env->was_reset = true;
+    int32_t bad = 0;
+    BPP_CUDA(cudaMemcpyAsync(&bad, env->d_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    BPP_CUDA(cudaStreamSynchronize(st));
+    if (bad) return fail(BPP_ERR_INVALID, "bpp_import_state: " + std::to_string(bad) + " heights outside [0, H] (left unchanged)");
     return BPP_OK;
 }
 

@@ -92,6 +92,24 @@ __device__ __forceinline__ void store_out(T *p, T v)
     __stcs(p, v);
 }
 #endif
+// Build switch (on by default): the rollout instantiations for 10x10 bins move heightmap tiles, observation and mask
+// rows with bulk asynchronous copies (see "Bulk asynchronous copies" below and the kernel in bpp_step.cu).
+#ifndef BPP_TMA
+#define BPP_TMA 1
+#endif
+constexpr bool kTmaBuild = BPP_TMA != 0;
+// bins per warp batch of that path (log2): bounded by shared memory -- a batch's tiles and staged records live there.
+// Measured on a B200 (profiles/r2c_ab_tma_variants.jsonl): without rotation 32-bin batches at 3 CTAs per SM beat 16-bin
+// batches at 5 (the lane-per-bin phases are amortised over twice the bins, 0.239 vs 0.246 ms); with rotation -- twice
+// the sweep work per bin -- 16-bin batches at 4-5 CTAs win (0.315 vs 0.345 ms).
+// tma_bpw_log2 = the batch size of big envs; envs too small to fill the SMs with such batches take 16-bin batches.
+#ifndef BPP_TMA_BPW_LOG2
+#define BPP_TMA_BPW_LOG2 5
+#endif
+#ifndef BPP_TMA_BPW_LOG2_ROT
+#define BPP_TMA_BPW_LOG2_ROT 4
+#endif
+__host__ __device__ constexpr int tma_bpw_log2(int rot) { return rot ? BPP_TMA_BPW_LOG2_ROT : BPP_TMA_BPW_LOG2; }
 // bytes of the per-warp "pairs" array that the packed sweep reads (one 32-bit word per heightmap cell)
 __host__ __device__ constexpr int pair_bytes(int cs) { return kPackedSweep && cs > 0 ? 4 * ((cs * cs + 15) & ~15) : 0; }
 
@@ -153,6 +171,12 @@ struct StepIO {
     float *ratio;               // [N]
     long long *sample;          // [N]
     int episode_inc;            // reset: 1 if the env had been reset before (LoadBoxCreator.index += 1)
+    // Packed per-bin results (include/bpp_b200.h bpp_result, 16 bytes: reward f32 | placed volume i32 | counter i32 |
+    // next sampled action i32): one 128-bit store per bin instead of reward / counter / ratio / sample; `done` stays a
+    // separate byte array (the host reads it as np.bool_ without a pass over the records).
+    uint4 *packed;              // [N] or null
+    int n_steps;                // >= 1: env steps per launch; steps after the first take the previous step's sampled
+                                // action (policy-free rollouts; rs / replay only, needs `sample` or `packed`)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -224,6 +248,87 @@ __device__ __forceinline__ void st_global_u4(uint4 *p, uint4 v)
     asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 #endif
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Bulk asynchronous copies (TMA unit, SASS UBLKCP) and the mbarrier that tracks a load's completion (SYNCS).
+// The step kernel moves whole batches of heightmap tiles with them and lets the copy engine write the observation /
+// mask rows from shared memory, so that none of that traffic goes through the load/store unit.
+//   bulk_load  : global -> shared, completes on an mbarrier (complete_tx::bytes); issued by ONE lane
+//   bulk_store : shared -> global, tracked by the issuing thread's bulk async-group (commit / wait_group.read)
+//   fence_async_smem: makes this thread's ordinary shared-memory writes visible to the async proxy (before a
+//                bulk_store of that memory is issued by some lane after a __syncwarp)
+// Addresses and sizes are multiples of 16 bytes.  Under BPP_SIMT_EMUL (CPU interpretation, tests only) the copies
+// happen at issue time and the waits are no-ops; a __syncwarp() always separates the issue of a load from the first
+// wait on it, which is what makes that model faithful to the order the hardware guarantees.
+// ---------------------------------------------------------------------------------------------------
+// A shared-memory address as the copy engine takes it (32-bit shared-window address; the kernel converts its per-warp
+// pointers ONCE -- a generic-to-shared conversion per use costs two instructions per copy).
+#ifdef BPP_SIMT_EMUL
+typedef uint8_t *saddr_t;
+__device__ __forceinline__ saddr_t saddr(void *p) { return static_cast<uint8_t *>(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t) { *bar = 0ull; }
+__device__ __forceinline__ void fence_mbar_init() {}
+__device__ __forceinline__ void fence_async_smem() {}
+__device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, uint32_t bytes, unsigned long long *bar)
+{
+    std::memcpy(sdst, gsrc, bytes);
+    *bar += 1ull;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    if (((*bar + 1ull) & 1ull) != (unsigned long long)(parity & 1u)) simt::die("mbar_wait before the load of that phase was issued");
+}
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) { std::memcpy(gdst, ssrc, bytes); }
+__device__ __forceinline__ void bulk_load_s(saddr_t sdst, const void *gsrc, uint32_t bytes, saddr_t bar)
+{
+    bulk_load(sdst, gsrc, bytes, reinterpret_cast<unsigned long long *>(bar));
+}
+__device__ __forceinline__ void mbar_wait_s(saddr_t bar, uint32_t parity) { mbar_wait(reinterpret_cast<unsigned long long *>(bar), parity); }
+__device__ __forceinline__ void bulk_commit() {}
+template <int N> __device__ __forceinline__ void bulk_wait_read() {}
+__device__ __forceinline__ void bulk_wait_all() {}
+#else
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile("{\n .reg .pred p;\n BPP_MBAR_WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 " @p bra BPP_MBAR_DONE_%=;\n bra BPP_MBAR_WAIT_%=;\n BPP_MBAR_DONE_%=:\n}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+typedef uint32_t saddr_t;
+__device__ __forceinline__ saddr_t saddr(void *p) { return smem_u32(p); }
+__device__ __forceinline__ void bulk_load_s(saddr_t sdst, const void *gsrc, uint32_t bytes, saddr_t bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(saddr_t bar, uint32_t parity)
+{
+    asm volatile("{\n .reg .pred p;\n BPP_MBAR_WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 " @p bra BPP_MBAR_DONE_%=;\n bra BPP_MBAR_WAIT_%=;\n BPP_MBAR_DONE_%=:\n}"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *gdst, saddr_t ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+#endif
 
 // floor(q / d) == (q * c_rcp16[d]) >> 16 for q < 1024, 1 <= d <= 32  (c_rcp16[d] = ceil(2^16 / d))
 __constant__ uint32_t c_rcp16[kMaxSide + 1] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115, 2048};

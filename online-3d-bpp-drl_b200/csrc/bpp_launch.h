@@ -7,7 +7,7 @@ namespace bpp {
 
 // bpp_step.cu
 cudaError_t launch_step(const EnvParams &p, const StepIO &io, int mode, int rot, int variant, bool vec4, int num_sms,
-                        size_t smem, cudaStream_t st);
+                        cudaStream_t st);
 
 // bpp_gen.cu
 cudaError_t launch_gen(const EnvParams &p, int mode, uint32_t e0, int num_sms, cudaStream_t st);
@@ -23,7 +23,7 @@ cudaError_t launch_check_box(const int32_t *plain, const int32_t *query, int n, 
 cudaError_t launch_export_state(const EnvParams &p, int32_t *plain, int32_t *box, int32_t *counter, int32_t *vol,
                                 cudaStream_t st);
 cudaError_t launch_import_state(const EnvParams &p, const int32_t *plain, const int32_t *box, const int32_t *counter,
-                                const int32_t *vol, cudaStream_t st);
+                                const int32_t *vol, int32_t *bad, cudaStream_t st);
 cudaError_t launch_debug_draws(unsigned long long seed, uint32_t domain, uint32_t aux, unsigned long long gid, int n,
                                uint32_t *out, cudaStream_t st);
 

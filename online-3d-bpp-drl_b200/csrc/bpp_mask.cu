@@ -120,14 +120,16 @@ __global__ void bpp_export_kernel(EnvParams p, int32_t *plain, int32_t *box, int
 }
 
 __global__ void bpp_import_kernel(EnvParams p, const int32_t *plain, const int32_t *box, const int32_t *counter,
-                                  const int32_t *vol)
+                                  const int32_t *vol, int32_t *bad)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long cells = (long long)p.N * p.A;
     if (plain && t < cells) {
         const long long b = t / p.A;
         const int k = (int)(t - b * p.A);
-        p.hm[b * p.A_pad + k] = (uint8_t)plain[t];
+        const int32_t h = plain[t];
+        if (h < 0 || h > p.H) { if (bad) atomicAdd(bad, 1); }      // a height outside [0, H] cannot come from Space.plain
+        else p.hm[b * p.A_pad + k] = (uint8_t)h;
     }
     if (t < p.N) {
         BinScalars s = p.sc[t];
@@ -148,10 +150,10 @@ cudaError_t launch_export_state(const EnvParams &p, int32_t *plain, int32_t *box
 }
 
 cudaError_t launch_import_state(const EnvParams &p, const int32_t *plain, const int32_t *box, const int32_t *counter,
-                                const int32_t *vol, cudaStream_t st)
+                                const int32_t *vol, int32_t *bad, cudaStream_t st)
 {
     const long long n = (long long)p.N * p.A;
-    BPP_LAUNCH((bpp_import_kernel), (unsigned)((n + 255) / 256), 256, 0, st, p, plain, box, counter, vol);
+    BPP_LAUNCH((bpp_import_kernel), (unsigned)((n + 255) / 256), 256, 0, st, p, plain, box, counter, vol, bad);
     return cudaGetLastError();
 }
 

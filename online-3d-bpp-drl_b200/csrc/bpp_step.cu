@@ -9,14 +9,25 @@
 // issue slots 66 %, DRAM 56 %), see DESIGN.md section 3 and profiles/README.md.  Reference behaviour is cited inline
 // (paths relative to the reference root).
 #include <cstdlib>
+#include <mutex>
 
 #include "bpp_common.cuh"
 #include "bpp_launch.h"
 #include "bpp_params.h"
 
+// Build switch: also the ordinary (LDG/STG) instantiations take the warp index and the item through a warp reduction, which
+// moves their batch / row address arithmetic to the uniform datapath (54-60 instead of 64 registers).
+#ifndef BPP_UNIFORM
+#define BPP_UNIFORM 1
+#endif
+constexpr bool kUniformOps = BPP_UNIFORM != 0;
 #ifndef BPP_MIN_BLOCKS
 #define BPP_MIN_BLOCKS 4   // resident CTAs per SM the register allocator must allow (8 warps each)
 #endif
+// Resident CTAs per SM the register allocator must allow for the bulk-copy instantiations.  Their shared memory holds a
+// whole batch of tiles and records, so the batch size decides: 32-bin batches fit 3 CTAs per SM, 16-bin batches 5 (4 with
+// rotation).  Both are built; the launch picks per env size (launch_rv below).
+__host__ __device__ constexpr int tma_min_blocks(int rot, int bpw_log2) { return bpw_log2 >= 5 ? 3 : (rot ? 4 : 5); }
 
 namespace bpp {
 
@@ -24,6 +35,19 @@ __device__ __forceinline__ float4 bytes_to_float4(uint32_t w)
 {
     return make_float4((float)(w & 0xffu), (float)((w >> 8) & 0xffu), (float)((w >> 16) & 0xffu),
                        (float)(w >> 24));
+}
+
+// The three constant planes of an observation by ordinary stores (bulk-copy path, item sides beyond its table of planes).
+__device__ __noinline__ void store_planes_slow(float *o, int A, int bx, int by, int bz, int lane)
+{
+    const float fx = (float)bx, fy = (float)by, fz = (float)bz;
+    float4 *o4 = reinterpret_cast<float4 *>(o);
+    const int q4 = A >> 2;
+    for (int k = lane; k < q4; k += 32) {
+        store_out(o4 + q4 + k, make_float4(fx, fx, fx, fx));
+        store_out(o4 + 2 * q4 + k, make_float4(fy, fy, fy, fy));
+        store_out(o4 + 3 * q4 + k, make_float4(fz, fz, fz, fz));
+    }
 }
 
 constexpr int kRecQuads = 5;     // uint4 words per staged bin record
@@ -46,54 +70,90 @@ __device__ __forceinline__ uint32_t episode_item(const EnvParams &p, long long b
 // The kernel works on batches of 32 bins per warp (fewer for small N) in three phases:
 //   A  (lane = bin)   scalar work once per bin instead of once per lane: state record, action decode with bounds
 //                     test, Philox draws, both candidates for the next item (placement succeeds / episode ends) and
-//                     their count thresholds, the placement check itself for footprints of up to 32 cells (read from
-//                     global memory); everything is staged as an 80-byte record per bin in shared memory;
-//   B  (warp = bin)   for each bin of the batch in turn: record (two broadcast 128-bit loads), heightmap tile
-//                     (prefetched one bin ahead), footprint update (warp-cooperative check for larger footprints),
-//                     mask sweep, tile / observation / mask write-back, action sampling;
+//                     their count thresholds, the placement check itself for footprints of up to 32 cells;
+//                     everything is staged as an 80-byte record per bin in shared memory;
+//   B  (warp = bin)   for each bin of the batch in turn: record (two broadcast 128-bit loads), heightmap tile,
+//                     footprint update (warp-cooperative check for larger footprints), mask sweep, tile /
+//                     observation / mask write-back, action sampling;
 //   A2 (lane = bin)   reward, done, info, new state record, coalesced stores, episode metrics, generator refill list.
+//
+// Data movement comes in two flavours.  TMA = false (any bin size, any mode): tiles arrive by 128-bit LDG (prefetched
+// one bin ahead) and leave, like the observation and mask rows, by 128-bit STG.  TMA = true (the rollout
+// instantiations for 10x10 bins): the copy engine does it -- ONE bulk load per batch brings the batch's contiguous
+// tiles into shared memory (mbarrier-tracked; phase A's placement check then reads them there instead of from global
+// memory), the bins are updated in place, ONE bulk store per batch writes them back; per bin the float32 heightmap
+// plane and mask row are staged in shared memory and leave by bulk stores, and the three constant planes of the
+// observation are copied straight out of a per-CTA table of constant planes -- no LDS / STG at all for 3/5 of the bytes.
 //
 // Template parameters: ROT = enable_rotation, VARIANT = mask rule, VEC4 = 128-bit output stores possible,
 // CS = compile-time bin side (L == W == CS; 10 and 20 are the reference's configurations, 0 = any size read
 // from EnvParams), FAST = the rollout case (mode == step and every output requested) with the checks folded.
-template <int ROT, int VARIANT, bool VEC4, int CS, bool FAST>
-__global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(const EnvParams p, const StepIO io, const int mode_arg)
+template <int ROT, int VARIANT, bool VEC4, int CS, bool FAST, int TMA>
+__global__ void __launch_bounds__(kThreads, TMA ? tma_min_blocks(ROT, TMA) : BPP_MIN_BLOCKS) bpp_step_kernel(const EnvParams p, const StepIO io, const int mode_arg)
 {
+    static_assert(!TMA || (FAST && VEC4 && CS > 0), "the bulk-copy path is the rollout path of the compile-time bin sizes");
     const int mode = FAST ? (int)kModeStep : mode_arg;
-    const bool w_obs = FAST || io.obs != nullptr, w_mask = FAST || io.mask != nullptr, w_sample = FAST || io.sample != nullptr;
+    const bool w_obs = FAST || io.obs != nullptr, w_mask = FAST || io.mask != nullptr;
+    const bool w_sample = io.sample != nullptr || io.packed != nullptr;       // FAST: one of the two is there
     BPP_DYNAMIC_SMEM(smem);
     __shared__ unsigned long long blk_metrics[3];
-    __shared__ float4 plane_lut[256];                 // (v, v, v, v) for the constant x / y / z planes of the observation
+    __shared__ float4 plane_lut[TMA ? 1 : 256];       // (v, v, v, v) for the constant x / y / z planes of the observation
+    __shared__ __align__(8) unsigned long long tile_bar[kWarpsPerBlock];      // TMA: one mbarrier per warp
 
     const int lane = pinned((int)(threadIdx.x & 31));
     __builtin_assume(lane >= 0 && lane < 32);
-    const int warp = threadIdx.x >> 5;
+    // the warp index through a warp reduction: the compiler then knows it -- and the batch, bin and row addresses derived
+    // from it -- to be warp-uniform (uniform registers; the bulk copies take uniform operands)
+    const int warp = (TMA || kUniformOps) ? __reduce_max_sync(kFull, (int)(threadIdx.x >> 5)) : (int)(threadIdx.x >> 5);
     const int L = CS ? CS : p.L, W = CS ? CS : p.W, H = p.H, A = CS ? CS * CS : p.A;
     const int A_pad = CS ? ((CS * CS + 15) & ~15) : p.A_pad;
     const int M = A * (ROT ? 2 : 1), M_pad = CS ? ((CS * CS * (ROT ? 2 : 1) + 15) & ~15) : p.M_pad;
-    // per warp: heightmap tile | mask tile | (packed-sweep builds) complemented height pairs, one word per cell
     constexpr bool kPacked = kPackedSweep && CS > 0 && VARIANT == 2;
-    const int warp_bytes = A_pad + M_pad + pair_bytes(CS);
-    uint8_t *tile = smem + pinned(warp * warp_bytes);
-    uint8_t *smask = tile + A_pad;
-    uint32_t *pairs = reinterpret_cast<uint32_t *>(tile + A_pad + M_pad);
-    // per-warp record of the 32 bins of a batch: 20 words per bin, written in phase A, read in B and A2, so that
-    // the per-lane scalars do not occupy registers during the tile work
-    uint4 *rec = reinterpret_cast<uint4 *>(smem + kWarpsPerBlock * warp_bytes) + pinned(warp * (32 * kRecQuads));
-    uint4 *tile4 = reinterpret_cast<uint4 *>(tile);
+    // Shared memory.  Without TMA, per warp: heightmap tile | mask tile | pairs; then the 32 staged records per warp.
+    // With TMA, per warp: the batch's tiles | mask tile | pairs | f32 staging (heightmap plane, mask row) | records,
+    // and once per CTA the table of constant observation planes (values 0 .. CS).
+    constexpr int kTmaBins = TMA ? 1 << TMA : 32;        // TMA = log2 of the bins per warp batch (0: ordinary path)
+    constexpr int kTmaTiles = TMA ? kTmaBins * ((CS * CS + 15) & ~15) : 0;
+    constexpr int kTmaStage = TMA ? 4 * CS * CS * (ROT ? 3 : 2) : 0;
+    constexpr int kTmaLutN = CS + 1;                  // constant planes for the values 0 .. CS (item sides up to the bin side)
+    constexpr int kTmaLutBytes = TMA ? kTmaLutN * 4 * CS * CS : 0;
+    const int warp_bytes = TMA ? kTmaTiles + M_pad + pair_bytes(CS) + kTmaStage + kTmaBins * (16 * kRecQuads)
+                               : A_pad + M_pad + pair_bytes(CS);
+    uint8_t *wbase = smem + kTmaLutBytes + pinned(warp * warp_bytes);
+    uint8_t *tiles = wbase;                                             // TMA: the batch's tiles; else the one tile
+    uint8_t *smask = wbase + (TMA ? kTmaTiles : A_pad);
+    uint32_t *pairs = reinterpret_cast<uint32_t *>(smask + M_pad);
+    float4 *stage_hm = reinterpret_cast<float4 *>(smask + M_pad + pair_bytes(CS));
+    float4 *stage_mask = stage_hm + (CS * CS) / 4;
+    uint4 *rec = TMA ? reinterpret_cast<uint4 *>(smask + M_pad + pair_bytes(CS) + kTmaStage)
+                     : reinterpret_cast<uint4 *>(smem + kWarpsPerBlock * warp_bytes) + pinned(warp * (32 * kRecQuads));
     uint4 *smask4 = reinterpret_cast<uint4 *>(smask);
+    // shared-window addresses for the copy engine, converted once (warp-uniform)
+    const saddr_t sa_lut = saddr(smem), sa_tiles = saddr(tiles), sa_stage_hm = saddr(stage_hm), sa_stage_mask = saddr(stage_mask),
+                  sa_bar = saddr(&tile_bar[warp]);
     const int nq_tile = A_pad >> 4, nq_mask = M_pad >> 4;     // 128-bit words per tile
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
     const uint32_t rcpW = rcp16((uint32_t)W);
     const bool fresh_reset = mode == kModeReset && !io.episode_inc;
 
     if (threadIdx.x < 3) blk_metrics[threadIdx.x] = 0ull;
-    for (int v = threadIdx.x; v < 256; v += kThreads) {
-        const float f = (float)v;
-        plane_lut[v] = make_float4(f, f, f, f);
+    if constexpr (TMA != 0) {
+        float4 *lut = reinterpret_cast<float4 *>(smem);
+        for (int k = threadIdx.x; k < kTmaLutBytes / 16; k += kThreads) {
+            const float f = (float)(k / (CS * CS / 4));
+            lut[k] = make_float4(f, f, f, f);
+        }
+        fence_async_smem();                               // the table is only ever read by the copy engine
+        if (lane == 0) { mbar_init(&tile_bar[warp], 1); fence_mbar_init(); }
+    } else {
+        for (int v = threadIdx.x; v < 256; v += kThreads) {
+            const float f = (float)v;
+            plane_lut[v] = make_float4(f, f, f, f);
+        }
     }
     __syncthreads();
     unsigned long long m_ep = 0, m_cnt = 0, m_vol = 0;
+    uint32_t tile_phase = 0;                              // TMA: parity of the mbarrier phase the next load completes
 
     // bins per warp batch: 32 when there are plenty of bins, fewer (power of two) for small N so that the
     // batches still spread over all SMs instead of serialising 32 bins on a few warps
@@ -104,6 +164,9 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
 #else
     const long long n_batches = ((long long)p.N + (1 << bpw_log2) - 1) >> bpw_log2;
 #endif
+    const int n_steps = FAST ? max(io.n_steps, 1) : 1;
+#pragma unroll 1
+    for (int step = 0; step < n_steps; ++step) {
     for (long long batch = (long long)blockIdx.x * kWarpsPerBlock + warp; batch < n_batches;
          batch += (long long)gridDim.x * kWarpsPerBlock) {
 #if BPP_TWO_TIER
@@ -117,6 +180,14 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
         const bool have = lane < nb;
         const long long mybin = have ? bin0 + lane : bin0;
         const unsigned long long gid = p.global_offset + (unsigned long long)mybin;
+        uint8_t *hm0 = pinned_ptr(p.hm + (size_t)bin0 * A_pad);
+        if (TMA) {
+            // the batch's tiles: one bulk load (the bulk store of this warp's previous batch must have read them out)
+            if (lane == 0) {
+                if (n_steps > 1) bulk_wait_all(); else bulk_wait_read<0>();
+                bulk_load_s(sa_tiles, hm0, (uint32_t)(nb * A_pad), sa_bar);
+            }
+        }
 
         // ---- phase A: lane = bin ----------------------------------------------------------------------
         {
@@ -127,9 +198,17 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             const uint4 a = sp[0], b = sp[1];
             s.box = a.x; s.cnt = (int)a.y; s.vol = (int)a.z; s.episode = a.w;
             s.ctr = b.x; s.pos = (int)b.y; s.ep_len = (int)b.z; s.traj = b.w;
-            if (mode == kModeStep) action = io.actions[mybin];
+            if (mode == kModeStep) {
+                if (step == 0) action = io.actions[mybin];
+                else action = io.sample ? io.sample[mybin] : (long long)(int)io.packed[mybin].w;   // written by this lane one step ago
+            }
         }
         if (fresh_reset) { s.episode = 0; s.ctr = 0; }
+        if (TMA) {
+            __syncwarp();
+            mbar_wait_s(sa_bar, tile_phase);
+            tile_phase ^= 1u;
+        }
         // action decode, envs/bpp0/bin3D.py:100-105 (strict '>': action == A stays un-rotated and falls out
         // of bounds; without rotation an action > A trips the reference's assert, here it is infeasible),
         // Space.idx_to_position (space.py:153-156), orientation (space.py:166-172) and the bounds test of
@@ -148,10 +227,10 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                     thr_cur = pack_thresholds(x * y);
                     if (kLaneCheck && x * y <= 32) {
                         // Space.check_box (space.py:116-144) by this lane alone, on the bin's heightmap in global
-                        // memory (the sectors are re-read from L1 by the tile load of phase B).  The verdict and the
-                        // new height of the footprint replace the in-bounds flag: act bit 22 = placed,
-                        // bits 24..31 = max_h + z, bit 23 = decided here.
-                        const uint8_t *w = p.hm + (size_t)mybin * A_pad + idx;
+                        // memory (the sectors are re-read from L1 by the tile load of phase B) -- with TMA, on the
+                        // batch's tiles in shared memory.  The verdict and the new height of the footprint replace
+                        // the in-bounds flag: act bit 22 = placed, bits 24..31 = max_h + z, bit 23 = decided here.
+                        const uint8_t *w = (TMA ? tiles + lane * A_pad : p.hm + (size_t)mybin * A_pad) + idx;
                         const int z = (s.box >> 16) & 0xff;
                         const int c00 = w[0], c10 = w[(x - 1) * W], c01 = w[y - 1], c11 = w[(x - 1) * W + y - 1];
                         int m, cnt;
@@ -201,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
         if (have && w_sample) u_samp = draw(p.seed_lo, p.seed_hi, kDomSample, 0, gid, s.ctr);
         // stage the per-lane results: {box, act, thr_cur, next_ok} {next_new, thr_ok, thr_new, u_samp}
         // {cnt, vol, episode, ctr} {pos, ep_len, traj, traj_new} {len_new, result, -, -}
-        {
+        if (!TMA || lane < kTmaBins) {
             uint4 *r = rec + lane * kRecQuads;
             r[0] = make_uint4(s.box, act, thr_cur, next_ok);
             r[1] = make_uint4(next_new, thr_ok, thr_new, u_samp);
@@ -211,13 +290,12 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
         }
         }
         __syncwarp();
-        uint8_t *hm0 = pinned_ptr(p.hm + (size_t)bin0 * A_pad);
         float *obs0 = w_obs ? pinned_ptr(io.obs + (size_t)bin0 * 4 * A) : nullptr;
         float *mask0 = w_mask ? pinned_ptr(io.mask + (size_t)bin0 * M) : nullptr;
 
         // ---- phase B: warp = bin ----------------------------------------------------------------------
         uint4 pre = zero4;        // next bin's tile words, prefetched while the current bin is processed
-        const bool use_pre = nq_tile <= 32 && mode != kModeReset;
+        const bool use_pre = !TMA && nq_tile <= 32 && mode != kModeReset;
         if (use_pre && lane < nq_tile) pre = ld_global_u4(reinterpret_cast<const uint4 *>(hm0) + lane);
 #pragma unroll 1
         for (int b = 0; b < nb; ++b) {
@@ -225,17 +303,23 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             const uint32_t box = r0.x, bact = r0.y, b_thr_cur = r0.z, b_ok = r0.w;
             const uint32_t b_new = r1.x, b_thr_ok = r1.y, b_thr_new = r1.z, b_us = r1.w;
             uint8_t *ghm = hm0 + (unsigned)b * (unsigned)A_pad;
-            if (use_pre) {
-                if (lane < nq_tile) tile4[lane] = pre;
-                if (b + 1 < nb && lane < nq_tile) pre = ld_global_u4(reinterpret_cast<const uint4 *>(ghm + A_pad) + lane);
-            } else {
+            uint8_t *tile = TMA ? tiles + (unsigned)b * (unsigned)A_pad : tiles;   // TMA: updated in place
+            uint4 *tile4 = reinterpret_cast<uint4 *>(tile);
+            if (!TMA) {
+                if (use_pre) {
+                    if (lane < nq_tile) tile4[lane] = pre;
+                    if (b + 1 < nb && lane < nq_tile) pre = ld_global_u4(reinterpret_cast<const uint4 *>(ghm + A_pad) + lane);
+                } else {
 #pragma unroll 1
-                for (int k = lane; k < nq_tile; k += 32)
-                    tile4[k] = mode == kModeReset ? zero4 : ld_global_u4(reinterpret_cast<const uint4 *>(ghm) + k);
+                    for (int k = lane; k < nq_tile; k += 32)
+                        tile4[k] = mode == kModeReset ? zero4 : ld_global_u4(reinterpret_cast<const uint4 *>(ghm) + k);
+                }
             }
+            if (!TMA) {
 #pragma unroll 1
-            for (int k = lane; k < nq_mask; k += 32) smask4[k] = zero4;
-            __syncwarp();
+                for (int k = lane; k < nq_mask; k += 32) smask4[k] = zero4;
+                __syncwarp();
+            }
 
             bool succ = false;
             if (mode == kModeStep) {
@@ -296,10 +380,16 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                     for (int k = lane; k < nq_tile; k += 32) tile4[k] = zero4;  // Space(*bin_size), bin3D.py:57
                 }
             }
-            const uint32_t nbox = mode == kModeObserve ? box : (succ ? b_ok : b_new);
+            const uint32_t nbox_v = mode == kModeObserve ? box : (succ ? b_ok : b_new);
+            const uint32_t nbox = (TMA || kUniformOps) ? __reduce_max_sync(kFull, nbox_v) : nbox_v;     // (the same in every lane) warp-uniform for the compiler
             const uint32_t nthr = mode == kModeObserve ? pack_thresholds((int)(box & 0xff) * (int)((box >> 8) & 0xff))
                                                        : (succ ? b_thr_ok : b_thr_new);
             __syncwarp();
+            if (TMA) {      // (the previous bin's action sampler has read the mask tile: every lane is past the barrier above)
+#pragma unroll 1
+                for (int k = lane; k < nq_mask; k += 32) smask4[k] = zero4;
+                if (!kPacked) __syncwarp();
+            }
 
             // ground-truth mask of the new state
             const int bx = nbox & 0xff, by = (nbox >> 8) & 0xff, bz = (nbox >> 16) & 0xff;
@@ -323,10 +413,39 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                     for (int k = lane; k < (A >> 2); k += 32) d32[k] = s32[k];
                     total *= 2;
                 }
+                if (TMA && lane == 0) bulk_wait_read<0>();         // the previous bin's rows have left the staging area
                 __syncwarp();
             }
 
             // write back
+            if (TMA) {
+                // cur_observation, bin3D.py:61-66, and the mask with its all-ones fallback, utils.py:59-60,89-92:
+                // the float32 heightmap plane and the mask row are staged, then five bulk stores (one lane) write the
+                // bin's rows; the three constant planes come from the table of constant planes.
+                const uint32_t *t32 = reinterpret_cast<const uint32_t *>(tile);
+                const uint32_t *s32 = reinterpret_cast<const uint32_t *>(smask);
+#pragma unroll 1
+                for (int k = lane; k < (A >> 2); k += 32) stage_hm[k] = bytes_to_float4(t32[k]);
+#pragma unroll 1
+                for (int k = lane; k < (M >> 2); k += 32)
+                    stage_mask[k] = total == 0 ? make_float4(1.f, 1.f, 1.f, 1.f) : bytes_to_float4(s32[k]);
+                fence_async_smem();
+                __syncwarp();
+                float *o = obs0 + (unsigned)b * (unsigned)(4 * A);
+                float *mo = mask0 + (unsigned)b * (unsigned)M;
+                const bool in_lut = max(max(bx, by), bz) < kTmaLutN;
+                if (lane == 0) {
+                    bulk_store(o, sa_stage_hm, 4 * A);
+                    if (in_lut) {
+                        bulk_store(o + A, sa_lut + bx * (4 * A), 4 * A);
+                        bulk_store(o + 2 * A, sa_lut + by * (4 * A), 4 * A);
+                        bulk_store(o + 3 * A, sa_lut + bz * (4 * A), 4 * A);
+                    }
+                    bulk_store(mo, sa_stage_mask, 4 * M);
+                    bulk_commit();
+                }
+                if (!in_lut) store_planes_slow(o, A, bx, by, bz, lane);   // item sides beyond the table (never with the reference's item sets)
+            } else {
             if (mode != kModeObserve)
 #pragma unroll 1
                 for (int k = lane; k < nq_tile; k += 32) st_global_u4(reinterpret_cast<uint4 *>(ghm) + k, tile4[k]);
@@ -365,6 +484,7 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                     for (int k = lane; k < M; k += 32) store_out(mo + k, total == 0 ? 1.f : (float)smask[k]);
                 }
             }
+            }
             uint32_t pick = 0;
             if (w_sample) {   // uniform over mask == 1 (over all M entries under the fallback)
                 if (total == 0) {
@@ -387,7 +507,16 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                 }
             }
             if (lane == 0) reinterpret_cast<uint32_t *>(rec + b * kRecQuads + 4)[1] = pick | (succ ? 0x80000000u : 0u);
+            if (!TMA) __syncwarp();     // (bulk-copy path: nothing of the next bin touches this bin's scratch before its first barrier)
+        }
+        if (TMA) {
+            // the batch's tiles, updated in place, go back with one bulk store
+            fence_async_smem();
             __syncwarp();
+            if (lane == 0) {
+                bulk_store(hm0, sa_tiles, (uint32_t)(nb * A_pad));
+                bulk_commit();
+            }
         }
 
         // ---- phase A2: lane = bin ---------------------------------------------------------------------
@@ -396,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
         uint32_t next_ok, next_new, traj_new, my_res;
         int len_new;
         {
-            const uint4 *r = rec + lane * kRecQuads;
+            const uint4 *r = rec + (TMA ? (lane & (kTmaBins - 1)) : lane) * kRecQuads;
             const uint4 a = r[0], b1 = r[1], c = r[2], d = r[3], e4 = r[4];
             s.box = a.x; next_ok = a.w; next_new = b1.x;
             s.cnt = (int)c.x; s.vol = (int)c.y; s.episode = c.z; s.ctr = c.w;
@@ -418,10 +547,14 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             }
             finished = have && !succ;                                            // bin3D.py:108-112
             if (have) {
-                if (FAST || io.reward) io.reward[mybin] = reward;
+                if (io.packed) {
+                    st_global_u4(io.packed + mybin, make_uint4(__float_as_uint(reward), (uint32_t)s.vol, (uint32_t)s.cnt, my_res & 0x7fffffffu));
+                } else {
+                    if (FAST || io.reward) io.reward[mybin] = reward;
+                    if (FAST || io.counter) io.counter[mybin] = s.cnt;
+                    if (FAST || io.ratio) io.ratio[mybin] = __fdiv_rn((float)s.vol, p.lwh_f);
+                }
                 if (FAST || io.done) io.done[mybin] = succ ? 0 : 1;
-                if (FAST || io.counter) io.counter[mybin] = s.cnt;
-                if (FAST || io.ratio) io.ratio[mybin] = __fdiv_rn((float)s.vol, p.lwh_f);
             }
             const unsigned fin = __ballot_sync(kFull, finished);
             if (fin) {
@@ -438,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
             } else {
                 s.box = next_ok;
             }
-            if (w_sample) io.sample[mybin] = (long long)(my_res & 0x7fffffffu);
+            if (io.sample) io.sample[mybin] = (long long)(my_res & 0x7fffffffu);
             uint4 *sp = reinterpret_cast<uint4 *>(p.sc + mybin);
             sp[0] = make_uint4(s.box, (uint32_t)s.cnt, (uint32_t)s.vol, s.episode);
             sp[1] = make_uint4(s.ctr + 1u, (uint32_t)s.pos, (uint32_t)s.ep_len, s.traj);
@@ -455,7 +588,10 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
                 if (refill) p.gen_list[base + __popc(rb & ((1u << lane) - 1u))] = (int32_t)(p.ep_bin0 + mybin);
             }
         }
+        if (n_steps > 1) __syncwarp();      // the next step of this warp's bins reads what its lanes just wrote
     }
+    }
+    if (TMA && lane == 0) bulk_wait_all();  // shared memory must outlive the copy engine's reads
 
     // ---- episode metrics: registers -> shared -> one global atomic triple per CTA -------------------
     if (mode == kModeStep && p.metrics) {
@@ -467,38 +603,48 @@ __global__ void __launch_bounds__(kThreads, BPP_MIN_BLOCKS) bpp_step_kernel(cons
     }
 }
 
-// One launch: persistent CTAs (one wave of resident blocks, grid-stride over 32-bin batches).
-template <int ROT, int VARIANT, bool VEC4, int CS, bool FAST>
-static cudaError_t launch_t(const EnvParams &p, const StepIO &io, int mode, int num_sms, size_t smem, cudaStream_t st)
+// One launch: persistent CTAs (one wave of resident blocks, grid-stride over the warp batches).
+template <int ROT, int VARIANT, bool VEC4, int CS, bool FAST, int TMA>
+static cudaError_t launch_t(const EnvParams &p, const StepIO &io, int mode, int num_sms, cudaStream_t st)
 {
-    static int blocks_per_sm[64] = {0};                 // per device, for the shared-memory size of the last launch
+    // per device and instantiation: resident CTAs per SM for the shared-memory size of the last launch
+    static int blocks_per_sm[64] = {0};
     static size_t smem_seen[64] = {0}, smem_opted[64] = {0};
+    static std::mutex mu;                                 // two host threads may drive envs on one device
+    const size_t smem = step_smem_bytes(p, TMA, ROT);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     dev &= 63;
-    if (blocks_per_sm[dev] == 0 || smem_seen[dev] != smem) {
-        if (smem > 40 * 1024 && smem > smem_opted[dev]) {   // large bins: opt in to more than the default dynamic limit
-            e = cudaFuncSetAttribute(bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int resident;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (blocks_per_sm[dev] == 0 || smem_seen[dev] != smem) {
+            if (smem > 40 * 1024 && smem > smem_opted[dev]) {   // opt in to more than the default dynamic limit
+                e = cudaFuncSetAttribute(bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST, TMA>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                smem_opted[dev] = smem;
+            }
+            int b = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST, TMA>, kThreads, smem);
             if (e != cudaSuccess) return e;
-            smem_opted[dev] = smem;
+            blocks_per_sm[dev] = b > 0 ? b : 1;
+            smem_seen[dev] = smem;
         }
-        int b = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST>, kThreads, smem);
-        if (e != cudaSuccess) return e;
-        blocks_per_sm[dev] = b > 0 ? b : 1;
-        smem_seen[dev] = smem;
+        resident = blocks_per_sm[dev];
     }
-    const long long cap = (long long)num_sms * blocks_per_sm[dev];
-    // largest power-of-two batch (<= 32 bins per warp) that still gives at least 80 % of the resident warps a batch
+    const long long cap = (long long)num_sms * resident;
+    // largest power-of-two batch (<= 32 bins per warp; <= 2^TMA on the bulk-copy path, whose shared memory
+    // holds a batch's tiles) that still gives at least 80 % of the resident warps a batch
     // (measured at 65 536 bins: 16 bins per warp beat 8 and 32)
     EnvParams q = p;
-    q.bpw_log2 = 5;
+    q.bpw_log2 = TMA ? TMA : 5;
     while (q.bpw_log2 > 0 && (((long long)p.N + (1 << q.bpw_log2) - 1) >> q.bpw_log2) < (cap * kWarpsPerBlock * 4) / 5) --q.bpw_log2;
     {   // experiment hook: BPP_BPW_LOG2=k forces 2^k bins per warp batch
         static const char *force = std::getenv("BPP_BPW_LOG2");
         if (force && force[0] >= '0' && force[0] <= '5') q.bpw_log2 = force[0] - '0';
+        if (TMA && q.bpw_log2 > TMA) q.bpw_log2 = TMA;
     }
 #if BPP_TWO_TIER
     const BatchPlan plan = choose_batches(p.N, cap * kWarpsPerBlock);
@@ -509,31 +655,40 @@ static cudaError_t launch_t(const EnvParams &p, const StepIO &io, int mode, int 
 #endif
     const long long want = (batches + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int grid = (int)(want < cap ? want : cap);
-    BPP_LAUNCH((bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST>), grid, kThreads, smem, st, q, io, mode);
+    BPP_LAUNCH((bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST, TMA>), grid, kThreads, smem, st, q, io, mode);
     return cudaGetLastError();
 }
 
 template <int ROT, int VARIANT>
-static cudaError_t launch_rv(const EnvParams &p, const StepIO &io, int mode, bool vec4, int num_sms, size_t smem,
-                             cudaStream_t st)
+static cudaError_t launch_rv(const EnvParams &p, const StepIO &io, int mode, bool vec4, int num_sms, cudaStream_t st)
 {
-    const bool fast = mode == kModeStep && io.obs && io.mask && io.reward && io.done && io.counter && io.ratio && io.sample;
+    const bool fast = mode == kModeStep && io.obs && io.mask && io.done &&
+                      ((io.reward && io.counter && io.ratio && io.sample) || io.packed);
     const int cs = (vec4 && p.L == p.W && (p.L == 10 || p.L == 20)) ? p.L : 0;
-    if (cs == 10) return fast ? launch_t<ROT, VARIANT, true, 10, true>(p, io, mode, num_sms, smem, st)
-                              : launch_t<ROT, VARIANT, true, 10, false>(p, io, mode, num_sms, smem, st);
-    if (cs == 20) return fast ? launch_t<ROT, VARIANT, true, 20, true>(p, io, mode, num_sms, smem, st)
-                              : launch_t<ROT, VARIANT, true, 20, false>(p, io, mode, num_sms, smem, st);
-    return vec4 ? launch_t<ROT, VARIANT, true, 0, false>(p, io, mode, num_sms, smem, st)
-                : launch_t<ROT, VARIANT, false, 0, false>(p, io, mode, num_sms, smem, st);
+    if (cs == 10 && fast && kTmaBuild && !BPP_TWO_TIER) {
+        // bulk-copy path.  Big envs without rotation: 32-bin batches (3 CTAs per SM) while they still give 80 % of those
+        // warps a batch; otherwise 16-bin batches at 4-5 CTAs per SM (measured: profiles/r2d_ab_trimmed.jsonl).
+        constexpr int kBig = tma_bpw_log2(ROT);
+        const long long warps_big = (long long)num_sms * tma_min_blocks(ROT, kBig) * kWarpsPerBlock;
+        if (kBig > 4 && (((long long)p.N + (1 << kBig) - 1) >> kBig) >= (warps_big * 4) / 5)
+            return launch_t<ROT, VARIANT, true, 10, true, kBig>(p, io, mode, num_sms, st);
+        return launch_t<ROT, VARIANT, true, 10, true, 4>(p, io, mode, num_sms, st);
+    }
+    if (cs == 10) return fast ? launch_t<ROT, VARIANT, true, 10, true, 0>(p, io, mode, num_sms, st)
+                              : launch_t<ROT, VARIANT, true, 10, false, 0>(p, io, mode, num_sms, st);
+    if (cs == 20) return fast ? launch_t<ROT, VARIANT, true, 20, true, 0>(p, io, mode, num_sms, st)
+                              : launch_t<ROT, VARIANT, true, 20, false, 0>(p, io, mode, num_sms, st);
+    return vec4 ? launch_t<ROT, VARIANT, true, 0, false, 0>(p, io, mode, num_sms, st)
+                : launch_t<ROT, VARIANT, false, 0, false, 0>(p, io, mode, num_sms, st);
 }
 
 cudaError_t launch_step(const EnvParams &p, const StepIO &io, int mode, int rot, int variant, bool vec4, int num_sms,
-                        size_t smem, cudaStream_t st)
+                        cudaStream_t st)
 {
-    if (rot) return variant == 1 ? launch_rv<1, 1>(p, io, mode, vec4, num_sms, smem, st)
-                                 : launch_rv<1, 2>(p, io, mode, vec4, num_sms, smem, st);
-    return variant == 1 ? launch_rv<0, 1>(p, io, mode, vec4, num_sms, smem, st)
-                        : launch_rv<0, 2>(p, io, mode, vec4, num_sms, smem, st);
+    if (rot) return variant == 1 ? launch_rv<1, 1>(p, io, mode, vec4, num_sms, st)
+                                 : launch_rv<1, 2>(p, io, mode, vec4, num_sms, st);
+    return variant == 1 ? launch_rv<0, 1>(p, io, mode, vec4, num_sms, st)
+                        : launch_rv<0, 2>(p, io, mode, vec4, num_sms, st);
 }
 
 }  // namespace bpp

@@ -1,7 +1,8 @@
 """Puts the unmodified Python reference on sys.path (TEST INFRASTRUCTURE ONLY).
 
-The reference tree exists only in the build container (/root/reference); on the GPU box this
-returns None and callers must fall back to the committed fixtures under tests/golden/.
+The reference tree exists only in the build container (/root/reference).  Elsewhere the byte-for-byte copy of its
+`envs/`, `acktr/`, `baselines/` packages that oracle/make_ref.py vendors into oracle/_ref/ (git-ignored, shipped with
+the gpurun snapshot) is used; with neither this returns None and callers fall back to the fixtures under tests/golden/.
 """
 import contextlib
 import io
@@ -19,7 +20,10 @@ def reference_path():
             p = json.load(f).get("reference_path", "/root/reference")
     except OSError:
         p = "/root/reference"
-    return p if os.path.isdir(os.path.join(p, "envs", "bpp0")) else None
+    if os.path.isdir(os.path.join(p, "envs", "bpp0")):
+        return p
+    vendored = os.path.join(_HERE, "_ref")      # oracle/make_ref.py: byte-for-byte copy that travels to the GPU box
+    return vendored if os.path.isdir(os.path.join(vendored, "envs", "bpp0")) else None
 
 
 def load_reference():

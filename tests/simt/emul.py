@@ -57,7 +57,8 @@ class _Buffers(C.Structure):
 
 
 class _IO(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("actions", "obs", "mask", "reward", "done", "counter", "ratio", "sample")]
+    _fields_ = [(n, C.c_void_p) for n in ("actions", "obs", "mask", "reward", "done", "counter", "ratio", "sample", "packed")] + \
+               [("n_steps", C.c_int32)]
 
 
 _libs = {}
@@ -179,15 +180,26 @@ class EmulEnv(object):
         self.was_reset = False
         self.steps = 0
 
-    def _call(self, mode, actions=None, want_obs=True, want_mask=True, want_sample=True, scalars=True):
+    def _call(self, mode, actions=None, want_obs=True, want_mask=True, want_sample=True, scalars=True, packed=False,
+              n_steps=1):
+        """packed: results as 16-byte records (self.packed: reward f32 | vol i32 | counter i32 | next action i32) instead of
+        reward / counter / ratio / sample; n_steps: env steps in one launch (later steps take the sampled action)."""
         io = _IO()
+        io.n_steps = int(n_steps)
+        if packed and mode == 0:
+            if getattr(self, "packed", None) is None:
+                self.packed = _aligned((self.N, 4), np.int32)
+            io.packed = self.packed.ctypes.data
+            want_sample = want_sample and packed != "only"
         io.actions = None if actions is None else actions.ctypes.data
         io.obs = self.obs.ctypes.data if want_obs else None
         io.mask = self.mask.ctypes.data if want_mask else None
         io.sample = self.sample.ctypes.data if want_sample else None
         if mode == 0 and scalars:
-            io.reward, io.done = self.reward.ctypes.data, self.done.ctypes.data
-            io.counter, io.ratio = self.counter.ctypes.data, self.ratio.ctypes.data
+            io.done = self.done.ctypes.data
+            if not (packed and mode == 0):
+                io.reward = self.reward.ctypes.data
+                io.counter, io.ratio = self.counter.ctypes.data, self.ratio.ctypes.data
         rc = self._lib.emul_env_call(C.byref(self.cfg), C.byref(self.buf), C.byref(io), mode, int(self.was_reset),
                                      self.num_sms, self.blocks_per_sm)
         assert rc == 0

@@ -41,6 +41,8 @@ struct EmulIO {
     int32_t *counter;
     float *ratio;
     int64_t *sample;
+    void *packed;                // bpp_result[N] (16 B) or null
+    int32_t n_steps;             // env steps per launch (0 / 1 = one)
 };
 
 static EnvParams make_params(const bpp_config *cfg, const EmulBuffers *b)
@@ -77,14 +79,15 @@ int emul_env_call(const bpp_config *cfg, const EmulBuffers *b, const EmulIO *io_
     io.actions = reinterpret_cast<const long long *>(io_in->actions);
     io.obs = io_in->obs; io.mask = io_in->mask; io.reward = io_in->reward; io.done = io_in->done;
     io.counter = io_in->counter; io.ratio = io_in->ratio; io.sample = reinterpret_cast<long long *>(io_in->sample);
+    io.packed = static_cast<uint4 *>(io_in->packed);
+    io.n_steps = io_in->n_steps > 1 ? io_in->n_steps : 1;
     io.episode_inc = (mode == kModeReset && was_reset) ? 1 : 0;
     const bool cut = p.gen_kind >= 2;
     const int rot = cfg->rot ? 1 : 0;
     const bool vec4 = (p.A % 4 == 0) && (!io.obs || aligned16(io.obs)) && (!io.mask || aligned16(io.mask));
-    const size_t smem = step_smem_bytes(p);
     if (mode == kModeReset && cut && !was_reset)
         if (launch_gen(p, 0, 0u, num_sms, nullptr) != cudaSuccess) return -2;
-    if (launch_step(p, io, mode, rot, cfg->mask_variant, vec4, num_sms, smem, nullptr) != cudaSuccess) return -2;
+    if (launch_step(p, io, mode, rot, cfg->mask_variant, vec4, num_sms, nullptr) != cudaSuccess) return -2;
     if (cut && ((mode == kModeReset && was_reset) || mode == kModeStep))
         if (launch_gen(p, 1, 0u, num_sms, nullptr) != cudaSuccess) return -2;
     return 0;
@@ -114,7 +117,7 @@ int emul_export_state(const bpp_config *cfg, const EmulBuffers *b, int32_t *plai
 int emul_import_state(const bpp_config *cfg, const EmulBuffers *b, const int32_t *plain, const int32_t *box,
                       const int32_t *counter, const int32_t *vol)
 {
-    return launch_import_state(make_params(cfg, b), plain, box, counter, vol, nullptr);
+    return launch_import_state(make_params(cfg, b), plain, box, counter, vol, nullptr, nullptr);
 }
 
 int emul_debug_draws(unsigned long long seed, uint32_t domain, uint32_t aux, unsigned long long gid, int n, uint32_t *out)

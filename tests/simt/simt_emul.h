@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <vector>
 
 // ---- CUDA language keywords ----------------------------------------------------------------------------------------
@@ -29,6 +30,7 @@
 #define __global__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static              // blocks run one at a time, so a function-local static is per block
@@ -215,6 +217,7 @@ static inline int __ffs(uint32_t v) { return __builtin_ffs((int)v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 template <class T> static inline void __stcs(T *p, T v) { *p = v; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }       // IEEE single division (SSE), round to nearest
 static inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }

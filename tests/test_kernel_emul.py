@@ -260,3 +260,46 @@ def test_philox_streams():
         got = emul.debug_draws(seed, dom, aux, gid, 70)
         want = np.array([orc.draw(seed, dom, aux, gid, i) for i in range(70)], dtype=np.uint32)
         assert np.array_equal(got, want)
+
+
+NO_TMA = ("BPP_TMA=0",)
+
+
+@pytest.mark.parametrize("defines", [pytest.param((), id="tma"), pytest.param(NO_TMA, id="no-tma")])
+@pytest.mark.parametrize("rot", [False, True])
+def test_packed_results_and_multi_step_launch(rot, defines):
+    """bpp_result records (reward | placed volume | counter | next action) instead of four arrays, and K env steps in ONE
+    launch (policy-free rollouts: every step after the first takes the action the previous step sampled) against K single
+    steps of the oracle -- on the bulk-copy path (10x10, every output) and with that path compiled out."""
+    N, size, K = 150, (10, 10, 10), 5
+    for gen_kw in (dict(gen="rs"),):
+        e = emul.EmulEnv(N, size, rot=rot, seed=21, defines=defines, **gen_kw)
+        o = orc.OracleEnv(N, size, rot=rot, seed=21, n_threads=1, **gen_kw)
+        e.reset()
+        o.reset()
+        for rnd in range(3):
+            a0 = o.sample.copy()
+            e._call(0, np.ascontiguousarray(a0), packed=True, n_steps=K)
+            for _ in range(K):
+                o.step(o.sample.copy())
+            assert np.array_equal(e.obs, o.obs) and np.array_equal(e.mask, o.mask), rnd
+            rec = e.packed
+            assert np.array_equal(rec[:, 0].view(np.float32), o.reward)
+            assert np.array_equal(rec[:, 2], o.counter) and np.array_equal(rec[:, 3].astype(np.int64), o.sample)
+            assert np.array_equal(e.done, o.done)
+            vol = rec[:, 1].astype(np.float64) / 1000.0
+            assert np.max(np.abs(vol - o.ratio)) <= 1e-6
+            assert np.array_equal(e.sample, o.sample)          # `sample` is still written next to the records
+        for a, b in zip(e.get_state(), o.get_state()):
+            assert np.array_equal(a, b)
+        m = e.metrics_dict()
+        m["steps"] = o.metrics()["steps"]                      # the emulated env counts launches, not steps
+        assert m == o.metrics()
+
+
+def test_bulk_copy_path_32_bin_batches():
+    """Envs big enough to fill the SMs with 32-bin batches take the <.., TMA = 5> instantiation (3 CTAs per SM); with
+    2 emulated SMs that is 1216 bins.  Ragged last batch, several batches per warp, both mask rules."""
+    for variant in (2, 1):
+        run_against_oracle(1300, (10, 10, 10), False, variant, dict(gen="rs"), T=5, seed=77, edge_every=2, num_sms=2,
+                           blocks_per_sm=3)
