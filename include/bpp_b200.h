@@ -134,8 +134,9 @@ int32_t bpp_step_packed(bpp_env *env, const int64_t *actions, float *obs, float 
 
 /* Same with HOST results / done (pinned and mapped, e.g. from bpp_host_alloc: the kernel writes them in place over
  * PCIe; ordinary memory is staged through device copies).  actions_host may be pinned host memory (read in place),
- * ordinary host memory (staged) or a device pointer (a policy that lives on the GPU).  `sample` (device, may be NULL)
- * receives the next sampled action as int64 as well.  One step; synchronises `stream`. */
+ * ordinary host memory (staged) or a device pointer (a policy that lives on the GPU).  `sample` (device
+ * memory, or pinned mapped host memory such as the caller's next action buffer; may be NULL) receives the next sampled
+ * action as int64 as well.  One step; synchronises `stream`. */
 int32_t bpp_step_packed_host(bpp_env *env, const int64_t *actions_host, float *obs, float *mask,
                              bpp_result *results_host, uint8_t *done_host, int64_t *sample, void *stream);
 

@@ -48,7 +48,9 @@ class EpisodeStats(object):
 
     def update(self, done, counter, ratio):
         d = done.to(torch.float64)
-        r = ratio.to(torch.float64)
+        # `ratio` is float32(vol / LWH): the placed volume is an integer below 2^23, so rounding ratio * LWH recovers it
+        # exactly and the statistics are those of the reference's float64 arithmetic (space.py:146-151, monitor.py:64)
+        r = torch.round(ratio.to(torch.float64) * self.lwh) / self.lwh
         # episode return = 10 * ratio (sum of 10*v_i/LWH); length counts the failing step (monitor.py:62-64)
         self.acc += torch.stack([d.sum(), (d * r * 10.0).sum(), (d * (counter.to(torch.float64) + 1)).sum(), (d * r).sum()])
 

@@ -31,11 +31,13 @@ class LazyInfos(object):
 
     The reference builds N dicts per step (envs/bpp0/bin3D.py:111,123-125 + Monitor's 'episode' entry,
     baselines/bench/monitor.py:58-75); main.py:159-162 only reads those of finished episodes.  At
-    N = 2**19 a tuple of dicts per step is not an option, so dicts are built when indexed."""
+    N = 2**19 a tuple of dicts per step is not an option, so dicts are built when indexed -- from the step's
+    16-byte result records (include/bpp_b200.h bpp_result: placed volume and counter are integers, so `ratio`
+    and the episode return are exact float64 values, like the reference's)."""
 
-    def __init__(self, done, counter, ratio, lwh, t0, act_len):
-        self._done, self._counter, self._ratio = done, counter, ratio
-        self._lwh, self._t0, self._act_len = lwh, t0, act_len
+    def __init__(self, done, records, lwh, t0, act_len):
+        self._done, self._rec = done, records               # np.bool_[N], int32[N,4] view of the pinned records
+        self._lwh, self._t0, self._act_len = float(lwh), t0, act_len
 
     def __len__(self):
         return len(self._done)
@@ -43,11 +45,12 @@ class LazyInfos(object):
     def __getitem__(self, i):
         if isinstance(i, slice):
             return [self[k] for k in range(*i.indices(len(self)))]
-        info = {"counter": int(self._counter[i]), "ratio": float(self._ratio[i])}
+        vol, counter = int(self._rec[i, 1]), int(self._rec[i, 2])
+        info = {"counter": counter, "ratio": vol / self._lwh}              # space.py:146-151
         if self._done[i]:
-            info["mask"] = np.ones(self._act_len)                       # bin3D.py:111
+            info["mask"] = np.ones(self._act_len)                           # bin3D.py:111
             # Monitor: r = round(sum(rewards), 6) with rewards 10*vol_i/LWH; l counts the failing step
-            info["episode"] = {"r": round(10.0 * float(self._ratio[i]), 6), "l": int(self._counter[i]) + 1,
+            info["episode"] = {"r": round(10.0 * vol / self._lwh, 6), "l": counter + 1,
                                "t": round(time.time() - self._t0, 6)}
         return info
 
@@ -57,6 +60,27 @@ class LazyInfos(object):
 
     def done_indices(self):
         return np.flatnonzero(self._done)
+
+
+class _HostBuffer(object):
+    """Pinned, device-mapped host memory on the NUMA node of the env's GPU (bpp_host_alloc), viewed as numpy / torch."""
+
+    def __init__(self, lib, device_index, nbytes):
+        self._lib, self.nbytes = lib, int(nbytes)
+        ptr = C.c_void_p()
+        _cabi.check(lib.bpp_host_alloc(int(device_index), self.nbytes, C.byref(ptr)))
+        self.ptr = ptr.value
+        self._raw = (C.c_uint8 * self.nbytes).from_address(self.ptr)
+        self.u8 = np.frombuffer(self._raw, dtype=np.uint8)
+
+    def view(self, dtype, shape):
+        return self.u8.view(dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.u8 = self._raw = None
+            self._lib.bpp_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
 
 
 class BinPackingVecEnv(object):
@@ -132,12 +156,17 @@ class BinPackingVecEnv(object):
         self.counter_t = torch.zeros((N,), dtype=torch.int32, device=dev)
         self.ratio_t = torch.zeros((N,), dtype=torch.float32, device=dev)
         self.sample_t = torch.zeros((N,), dtype=torch.int64, device=dev) if want_sample else None
-        # pinned host mirrors for the reference-facing return values
-        self._h_actions = torch.empty((N,), dtype=torch.int64).pin_memory()
-        self._h_reward = torch.empty((N,), dtype=torch.float32).pin_memory()
-        self._h_done = torch.empty((N,), dtype=torch.uint8).pin_memory()
-        self._h_counter = torch.empty((N,), dtype=torch.int32).pin_memory()
-        self._h_ratio = torch.empty((N,), dtype=torch.float32).pin_memory()
+        # Host side of the reference-facing step(): pinned, device-mapped buffers next to this GPU.  Two result sets are
+        # used alternately, so what step() returned stays valid until the call after the next one.
+        di = cfg.device
+        self._hbufs = [_HostBuffer(self._lib, di, 8 * N)] + [_HostBuffer(self._lib, di, 16 * N) for _ in range(2)] + \
+                      [_HostBuffer(self._lib, di, N) for _ in range(2)]
+        self._h_actions = torch.from_numpy(self._hbufs[0].view(np.int64, (N,)))
+        self._h_rec = [self._hbufs[1 + k].view(np.int32, (N, 4)) for k in range(2)]
+        self._h_reward = [torch.from_numpy(self._hbufs[1 + k].view(np.float32, (N, 4)))[:, 0:1] for k in range(2)]
+        self._h_done = [self._hbufs[3 + k].view(np.bool_, (N,)) for k in range(2)]
+        self._flip = 0
+        self._dev_actions = None
         self._pending = None
         self._t0 = time.time()
         self.venv = None        # get_vec_normalize(envs) walks .venv and must end at None (acktr/utils.py:96-102)
@@ -155,6 +184,10 @@ class BinPackingVecEnv(object):
             torch.cuda.synchronize(self.device)
             self._lib.bpp_destroy(self._h)
             self._h = None
+            self._h_actions = self._h_rec = self._h_reward = self._h_done = None
+            for hb in getattr(self, "_hbufs", ()):
+                hb.free()
+            self._hbufs = ()
 
     def __del__(self):
         try:
@@ -185,33 +218,38 @@ class BinPackingVecEnv(object):
 
     # -- reference-facing VecEnv API (acktr/envs.py:170-193) -------------------------------------------
     def step_async(self, actions):
+        self._dev_actions = None
         if isinstance(actions, torch.Tensor):
             a = actions.reshape(-1)                                     # LongTensor[N,1] squeeze, envs.py:183-185
+            if a.numel() != self.num_envs:
+                raise ValueError("expected %d actions, got %d" % (self.num_envs, a.numel()))
             if a.is_cuda:
-                self._h_actions.copy_(a.to(torch.int64), non_blocking=True)   # .cpu() of envs.py:186
-                torch.cuda.current_stream(self.device).synchronize()
+                # a policy that lives on this GPU: the kernel reads its actions where they are (the reference's
+                # `.cpu()`, envs.py:186, has no counterpart here)
+                self._dev_actions = a if (a.dtype == torch.int64 and a.is_contiguous()) else a.to(torch.int64).contiguous()
             else:
-                self._h_actions.copy_(a.to(torch.int64))
+                self._h_actions.copy_(a)
         else:
             self._h_actions.copy_(torch.as_tensor(np.asarray(actions).reshape(-1), dtype=torch.int64))
         self._pending = True
 
     def step_wait(self):
+        """-> (obs float32[N,4LW] on the device, reward float32[N,1] on the CPU, done np.bool_[N], infos).
+        reward / done / infos are views of pinned host memory the kernel wrote over PCIe; they stay valid until the
+        second step() after this one."""
         assert self._pending, "step_wait without step_async"
         self._pending = None
+        k = self._flip
+        self._flip ^= 1
+        act = self._p(self._dev_actions) if self._dev_actions is not None else C.c_void_p(self._hbufs[0].ptr)
         with torch.cuda.device(self.device):
-            _cabi.check(self._lib.bpp_step_host(
-                self._h, self._p(self._h_actions), self._p(self.obs), self._p(self.location_masks),
-                self._p(self._h_reward), self._p(self._h_done), self._p(self._h_counter), self._p(self._h_ratio),
-                self._p(self.sample_t), self._stream()))
-        reward = self._h_reward.clone().unsqueeze(1)                     # float32[N,1] on the CPU, envs.py:192
-        done = self._h_done.numpy().astype(np.bool_)
-        if self.host_infos:
-            infos = LazyInfos(done, self._h_counter.numpy().copy(), self._h_ratio.numpy().copy(),
-                              float(np.prod(self.bin_size)), self._t0, self.act_len)
-        else:
-            infos = ()
-        return self.obs, reward, done, infos
+            _cabi.check(self._lib.bpp_step_packed_host(
+                self._h, act, self._p(self.obs), self._p(self.location_masks), C.c_void_p(self._hbufs[1 + k].ptr),
+                C.c_void_p(self._hbufs[3 + k].ptr), self._p(self.sample_t), self._stream()))
+        self._dev_actions = None
+        done = self._h_done[k]
+        infos = LazyInfos(done, self._h_rec[k], float(np.prod(self.bin_size)), self._t0, self.act_len) if self.host_infos else ()
+        return self.obs, self._h_reward[k], done, infos
 
     def step(self, actions):
         self.step_async(actions)

@@ -66,6 +66,73 @@ __device__ __forceinline__ void warp_erase(T *a, int idx, int n, int lane)
     }
 }
 
+// cut1 ordering phase for episodes of up to 64 pieces, held in registers: lane l owns pieces l and 32 + l.
+//
+// The reference keeps a shadow heightmap and calls a waiting piece ready when the map equals its lz on its whole
+// footprint (_add_candidate, cutCreator.py:98-107).  Pieces are emitted bottom-up and partition the bin exactly, so the
+// map equals lz on a cell exactly when the piece directly below it there -- whose top face is at lz -- has been
+// emitted: a piece is ready once the pieces whose top faces tile its bottom face have all been emitted.  Every piece
+// therefore carries the area of its bottom face still uncovered; emitting a piece whose top is at a waiting piece's lz
+// subtracts their overlap, and 0 means ready.  No shadow map, no footprint loops.  The candidate list is a position per
+// piece: candidates.pop(idx) selects the piece at position idx and moves the later ones down; pieces that become ready are
+// appended in meta_list order, i.e. by piece index (slot-major, lane-minor) -- the reference's orders exactly.
+__device__ int order_cut1_registers(const EnvParams &p, GenRng &g, uint32_t *out, const Piece *leaf, int n_leaf, int cap, int lane)
+{
+    const unsigned lt = (1u << lane) - 1u;
+    Piece q[2];
+    int rem[2], pos[2];                                  // uncovered bottom area (waiting pieces), candidate-list position
+    unsigned c[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int i = s * 32 + lane;
+        q[s] = i < n_leaf ? leaf[i] : 0;
+        const bool valid = i < n_leaf;
+        rem[s] = (valid && plz(q[s]) > 0) ? px(q[s]) * py(q[s]) : 0;
+        c[s] = __ballot_sync(kFull, valid && plz(q[s]) == 0);          // first scan: shadow == 0, ready <=> lz == 0
+    }
+    pos[0] = (c[0] >> lane) & 1u ? __popc(c[0] & lt) : -1;
+    pos[1] = (c[1] >> lane) & 1u ? __popc(c[0]) + __popc(c[1] & lt) : -1;
+    int n_cand = __popc(c[0]) + __popc(c[1]), n_out = 0;
+    while (n_cand > 0) {                                                  // :113-115: no candidate -> sentinel from now on
+        const int idx = (int)__umulhi(g.next(), (uint32_t)n_cand);        // random.randint(0, len(candidates) - 1), :116
+        const unsigned s0 = __ballot_sync(kFull, pos[0] == idx), s1 = __ballot_sync(kFull, pos[1] == idx);
+        const int src = __ffs(s0 | s1) - 1;
+        const Piece e = __shfl_sync(kFull, pos[0] == idx ? q[0] : q[1], src);      // candidates.pop(idx)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) pos[s] = pos[s] == idx ? -1 : (pos[s] > idx ? pos[s] - 1 : pos[s]);
+        --n_cand;
+        int ox = px(e), oy = py(e);
+        if (p.rot) {                                                      // :120-126
+            const uint32_t coin = g.next();
+            if (coin >= 0x80000000u) { ox = py(e); oy = px(e); }
+        }
+        if (n_out < cap) {
+            if (lane == 0) out[n_out] = pack_item(ox, oy, pz(e));
+            ++n_out;
+        }
+        // _update + _add_candidate, :109-110, :98-107
+        const int top = plz(e) + pz(e), ex0 = plx(e), ex1 = ex0 + px(e), ey0 = ply(e), ey1 = ey0 + py(e);
+        bool fresh[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            fresh[s] = false;
+            if (rem[s] > 0 && plz(q[s]) == top) {
+                const int wx = min(ex1, plx(q[s]) + px(q[s])) - max(ex0, plx(q[s]));
+                const int wy = min(ey1, ply(q[s]) + py(q[s])) - max(ey0, ply(q[s]));
+                if (wx > 0 && wy > 0) {
+                    rem[s] -= wx * wy;
+                    fresh[s] = rem[s] == 0;
+                }
+            }
+        }
+        const unsigned f0 = __ballot_sync(kFull, fresh[0]), f1 = __ballot_sync(kFull, fresh[1]);
+        if (fresh[0]) pos[0] = n_cand + __popc(f0 & lt);                  // candidates.append, in meta_list order
+        if (fresh[1]) pos[1] = n_cand + __popc(f0) + __popc(f1 & lt);
+        n_cand += __popc(f0) + __popc(f1);
+    }
+    return n_out;
+}
+
 // cut1, one warp per episode.  Phase 1, _cut_box (cutCreator.py:79-95), sweeps the piece list level by level, and
 // within one sweep the pieces are independent of each other except for WHICH two draws a piece that must be split
 // consumes (2 per split, in list order) and WHERE its one or two successors land in the next list -- two prefix sums.
@@ -131,6 +198,7 @@ __device__ int gen_cut1(const EnvParams &p, GenRng &g, uint32_t *out, Piece *lea
     g.blk_idx = 0xffffffffu;
 
     // ordering phase: generate_box_size / _add_candidate / _update, cutCreator.py:98-128
+    if (n_leaf <= 64) return order_cut1_registers(p, g, out, leaf, n_leaf, cap, lane);
     uint16_t *meta = lists, *cand = lists + cap;
     for (int i = lane; i < n_leaf; i += 32) meta[i] = (uint16_t)i;
     for (int k = lane; k < L * W; k += 32) shadow[k] = 0;
@@ -271,7 +339,147 @@ __device__ int gen_cut2(const EnvParams &p, GenRng &g, uint32_t *out, Piece *inv
     return n_out;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// cut2 with one LANE per episode (episodes of up to kLaneVal pieces, i.e. the reference's 10x10x10 configuration).
+// gen_benchmark's sweep (mdCreator.py:117-135) is sequential in the order of the random draws and has no data-parallel
+// part once list removal stops moving memory, so a warp runs 32 independent episodes: every lane keeps its own
+// `invalid_box` list (64-bit pieces) and `valid` list (x | y << 8 | z << 16 | lz << 24) in shared memory, element j of
+// lane l at index j * 32 + l (no bank conflicts while the lanes are in step).  invalid_box.remove(box) leaves a tombstone:
+// within a sweep the elements ahead of the iterator are all live, so "the iterator skips the element that slid into the
+// vacated slot" is simply i += 2; the list is compacted between sweeps.  The stable sort by low_bound (:137-138) is a
+// scan per level.  A lane whose lists would overflow flags its episode; the warp then redoes those with the cooperative
+// version above on the bin's global scratch.
+// ---------------------------------------------------------------------------------------------------
+#ifndef BPP_LANE_INV
+#define BPP_LANE_INV 64
+#endif
+#ifndef BPP_LANE_VAL
+#define BPP_LANE_VAL 128
+#endif
+constexpr int kLaneInv = BPP_LANE_INV, kLaneVal = BPP_LANE_VAL;     // list capacities per lane (tests shrink them to reach the fallback)
+constexpr int kLaneMaxCap = 128;                                    // envs with at most this many pieces per episode take this path
+constexpr int kLaneThreads = 64;
+constexpr size_t kLaneSmemPerWarp = 32 * ((size_t)kLaneInv * 8 + (size_t)kLaneVal * 4);
+
+__device__ __forceinline__ int gen_cut2_lane(const EnvParams &p, GenRng &g, uint32_t *out, int cap, Piece *inv, uint32_t *val,
+                                             int lane, bool &overflow)
+{
+#define BPP_INV(j) inv[(j) * 32 + lane]
+#define BPP_VAL(j) val[(j) * 32 + lane]
+    const int lo = p.lo[0], hi = p.hi[0];
+    int n_inv = 1, n_val = 0;
+    BPP_INV(0) = mk_piece(p.L, p.W, p.H, 0, 0, 0);
+    overflow = false;
+    while (n_inv > 0 && !overflow) {                                      // gen_benchmark, mdCreator.py:117-135
+        int i = 0, n_phys = n_inv;
+        while (i < n_phys) {
+            const Piece b = BPP_INV(i);
+            const unsigned fl = (unsigned)(px(b) > hi) | ((unsigned)(py(b) > hi) << 1) | ((unsigned)(pz(b) > hi) << 2);   // benchmark_split, :60-66
+            if (fl == 0u) {                                               // unreachable for validated ranges
+                BPP_INV(i) = 0;
+                if (n_val < kLaneVal) { BPP_VAL(n_val) = pack_item(px(b), py(b), pz(b)) | ((uint32_t)plz(b) << 24); ++n_val; }
+                else overflow = true;
+                i += 2;
+                continue;
+            }
+            const int r = (int)__umulhi(g.next(), (uint32_t)__popc(fl));  // random.choice(flags), :68: the r-th oversize axis
+            const unsigned rest = r == 0 ? fl : (r == 1 ? (fl & (fl - 1u)) : 4u);
+            const int ax = __ffs(rest) - 1;
+            const int side = ax == 0 ? px(b) : (ax == 1 ? py(b) : pz(b));
+            const int cut = 1 + (int)__umulhi(g.next(), (uint32_t)side);  // randint(1, side)
+            if (cut < lo || side - cut < lo) { ++i; continue; }            // rejected, retried in the next sweep
+            Piece sub[2];
+            if (ax == 0) { sub[0] = mk_piece(cut, py(b), pz(b), plx(b), ply(b), plz(b)); sub[1] = mk_piece(px(b) - cut, py(b), pz(b), plx(b) + cut, ply(b), plz(b)); }        // :70-79
+            else if (ax == 1) { sub[0] = mk_piece(px(b), cut, pz(b), plx(b), ply(b), plz(b)); sub[1] = mk_piece(px(b), py(b) - cut, pz(b), plx(b), ply(b) + cut, plz(b)); }   // :80-89
+            else { sub[0] = mk_piece(px(b), py(b), pz(b) - cut, plx(b), ply(b), plz(b)); sub[1] = mk_piece(px(b), py(b), cut, plx(b), ply(b), plz(b) + pz(b) - cut); }        // :90-99
+            BPP_INV(i) = 0;                                               // invalid_box.remove(box): tombstone
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {                                 // is_valid, :110-115
+                const Piece q = sub[s];
+                const bool ok = px(q) >= lo && px(q) <= hi && py(q) >= lo && py(q) <= hi && pz(q) >= lo && pz(q) <= hi;
+                if (ok) {
+                    if (n_val < kLaneVal) { BPP_VAL(n_val) = pack_item(px(q), py(q), pz(q)) | ((uint32_t)plz(q) << 24); ++n_val; }
+                    else overflow = true;
+                } else if (n_phys < kLaneInv) { BPP_INV(n_phys) = q; ++n_phys; }
+                else overflow = true;
+            }
+            if (overflow) break;
+            i += 2;                                                       // the iterator skips the element that slid into slot i
+        }
+        int k = 0;                                                        // drop the tombstones
+        for (int j = 0; j < n_phys; ++j) {
+            const Piece q = BPP_INV(j);
+            if (q != 0) { BPP_INV(k) = q; ++k; }
+        }
+        n_inv = k;
+    }
+    if (overflow) return 0;
+    int n_out = 0;                                                        // depart_box: stable sort by low_bound, :137-138
+    for (int level = 0; level <= p.H && n_out < cap; ++level)
+        for (int v = 0; v < n_val && n_out < cap; ++v) {
+            const uint32_t q = BPP_VAL(v);
+            if ((int)(q >> 24) == level) { out[n_out] = q & 0x00ffffffu; ++n_out; }
+        }
+    return n_out;
+#undef BPP_INV
+#undef BPP_VAL
+}
+
 }  // namespace
+
+// cut2, one lane per episode (see gen_cut2_lane).  mode 0 (init): work item w = bin (w >> 1), buffer / episode e0 + (w & 1);
+// mode 1 (refill): the bins on the refill list get episode sc.episode + 1 into the buffer they are not playing.
+__global__ void __launch_bounds__(kLaneThreads) bpp_gen_cut2_lane_kernel(const EnvParams p, const int mode, const uint32_t e0)
+{
+    BPP_DYNAMIC_SMEM(lane_smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Piece *inv = reinterpret_cast<Piece *>(lane_smem + (size_t)warp * kLaneSmemPerWarp);
+    uint32_t *val = reinterpret_cast<uint32_t *>(inv + 32 * kLaneInv);
+    const long long n_work = mode == 0 ? 2ll * p.N : (long long)*p.gen_count;
+    const long long n_threads = (long long)gridDim.x * blockDim.x;
+    // whole warps iterate together (the overflow fallback is warp-cooperative)
+    for (long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; w0 < n_work; w0 += n_threads) {
+        const long long w = w0 + lane;
+        const bool have = w < n_work;
+        long long bin = 0;
+        int buf = 0;
+        uint32_t episode = 0;
+        if (have) {
+            if (mode == 0) { bin = w >> 1; buf = (int)(w & 1); episode = e0 + (uint32_t)buf; }
+            else {
+                bin = (long long)p.gen_list[w];
+                const BinScalars s = p.sc[bin];
+                buf = (int)(s.traj & 1u) ^ 1;
+                episode = s.episode + 1u;
+            }
+        }
+        GenRng g;
+        g.seed_lo = p.seed_lo; g.seed_hi = p.seed_hi; g.aux = episode; g.k = 0; g.blk_idx = 0xffffffffu;
+        g.gid = p.global_offset + (unsigned long long)bin;
+        uint32_t *out = p.ep_items + ((size_t)buf * p.ep_buf_bins + (size_t)bin) * p.ep_cap;
+        bool overflow = false;
+        if (have) {
+            const int n = gen_cut2_lane(p, g, out, p.ep_cap, inv, val, lane, overflow);
+            if (!overflow) p.ep_len2[(size_t)buf * p.ep_buf_bins + (size_t)bin] = n;
+        }
+        unsigned ov = __ballot_sync(kFull, have && overflow);
+        while (ov) {                                                      // lists too long for a lane: the whole warp redoes the episode
+            const int src = __ffs(ov) - 1;
+            ov &= ov - 1;
+            const long long b2 = __shfl_sync(kFull, bin, src);
+            const int buf2 = __shfl_sync(kFull, buf, src);
+            GenRng g2;
+            g2.seed_lo = p.seed_lo; g2.seed_hi = p.seed_hi; g2.aux = __shfl_sync(kFull, episode, src); g2.k = 0; g2.blk_idx = 0xffffffffu;
+            g2.gid = p.global_offset + (unsigned long long)b2;
+            Piece *ginv = reinterpret_cast<Piece *>(p.gen_scratch + (size_t)b2 * (size_t)p.gen_scratch_stride);
+            const int n = gen_cut2(p, g2, p.ep_items + ((size_t)buf2 * p.ep_buf_bins + (size_t)b2) * p.ep_cap, ginv,
+                                   ginv + p.ep_cap + 64, p.ep_cap, lane);
+            if (lane == 0) p.ep_len2[(size_t)buf2 * p.ep_buf_bins + (size_t)b2] = n;
+            __syncwarp();
+        }
+    }
+}
 
 // One warp per episode.  mode 0 (init): every bin gets episode e0 into buffer 0 and e0 + 1 into buffer 1;
 // mode 1 (refill): the bins on the compacted refill list (appended by the step kernel at auto-reset) get episode
@@ -319,17 +527,34 @@ __global__ void __launch_bounds__(128) bpp_gen_kernel(const EnvParams p, const i
 
 cudaError_t launch_gen(const EnvParams &p, int mode, uint32_t e0, int num_sms, cudaStream_t st)
 {
-    long long want = ((long long)p.N + 3) / 4;            // 4 warps per block, one episode per warp
-    const long long cap = (long long)num_sms * 16;
-    if (mode == 1 && want > cap) want = cap;              // the list length is only known on the device
-    const size_t smem = (size_t)4 * (size_t)p.gen_scratch_stride;
-    const int use_smem = smem <= 200 * 1024;
-    if (use_smem && smem > 48 * 1024) {
-        cudaError_t ea = cudaFuncSetAttribute(bpp_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (ea != cudaSuccess) return ea;
+    cudaError_t e;
+    if (p.gen_kind == 3 && p.ep_cap <= kLaneMaxCap) {        // cut2 at the reference's bin sizes: one lane per episode
+        const size_t smem = (kLaneThreads / 32) * kLaneSmemPerWarp;
+        static bool opted[64] = {false};
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if (!opted[dev & 63]) {
+            e = cudaFuncSetAttribute(bpp_gen_cut2_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            opted[dev & 63] = true;
+        }
+        long long want = ((mode == 0 ? 2ll : 1ll) * p.N + kLaneThreads - 1) / kLaneThreads;
+        const long long cap = (long long)num_sms * 3;     // resident blocks (shared memory: three per SM)
+        if (want > cap) want = cap;
+        BPP_LAUNCH((bpp_gen_cut2_lane_kernel), (unsigned)want, kLaneThreads, smem, st, p, mode, e0);
+    } else {
+        long long want = ((long long)p.N + 3) / 4;        // 4 warps per block, one episode per warp
+        const long long cap = (long long)num_sms * 16;
+        if (mode == 1 && want > cap) want = cap;          // the list length is only known on the device
+        const size_t smem = (size_t)4 * (size_t)p.gen_scratch_stride;
+        const int use_smem = smem <= 200 * 1024;
+        if (use_smem && smem > 48 * 1024) {
+            e = cudaFuncSetAttribute(bpp_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        BPP_LAUNCH((bpp_gen_kernel), (unsigned)want, 128, use_smem ? smem : 0, st, p, mode, e0, use_smem);
     }
-    BPP_LAUNCH((bpp_gen_kernel), (unsigned)want, 128, use_smem ? smem : 0, st, p, mode, e0, use_smem);
-    cudaError_t e = cudaGetLastError();
+    e = cudaGetLastError();
     if (e != cudaSuccess || mode == 0) return e;
     return cudaMemsetAsync(p.gen_count, 0, sizeof(int32_t), st);     // list consumed
 }

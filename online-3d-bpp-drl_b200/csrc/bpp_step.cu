@@ -670,7 +670,11 @@ static cudaError_t launch_rv(const EnvParams &p, const StepIO &io, int mode, boo
         // warps a batch; otherwise 16-bin batches at 4-5 CTAs per SM (measured: profiles/r2d_ab_trimmed.jsonl).
         constexpr int kBig = tma_bpw_log2(ROT);
         const long long warps_big = (long long)num_sms * tma_min_blocks(ROT, kBig) * kWarpsPerBlock;
-        if (kBig > 4 && (((long long)p.N + (1 << kBig) - 1) >> kBig) >= (warps_big * 4) / 5)
+        static const char *force = std::getenv("BPP_TMA_FORCE");      // test hook: "5" / "4" picks the instantiation
+        const bool big = force && (force[0] == '4' || force[0] == '5')
+                             ? force[0] == '5'
+                             : (((long long)p.N + (1 << kBig) - 1) >> kBig) >= (warps_big * 4) / 5;
+        if (kBig > 4 && big)
             return launch_t<ROT, VARIANT, true, 10, true, kBig>(p, io, mode, num_sms, st);
         return launch_t<ROT, VARIANT, true, 10, true, 4>(p, io, mode, num_sms, st);
     }

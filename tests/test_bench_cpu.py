@@ -9,7 +9,7 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 def test_reference_arm_json_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3",
-                          "--warmup", "3", "--workload", "cfg1"], capture_output=True, text=True, timeout=300,
+                          "--warmup", "3", "--workload", "cfg1", "--ref-seconds", "3"], capture_output=True, text=True, timeout=300,
                          env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert out.returncode == 0, out.stderr
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
@@ -17,9 +17,15 @@ def test_reference_arm_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "env-steps/sec" and d["unit"] == "env-steps/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 3
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the reference itself (from /root/reference or its vendored copy oracle/_ref), not the C port
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert "ShmemVecEnv" in d["cpu_baseline"]["sample"] and d["subproc_step_only"]["value"] > d["subproc_step_and_mask"]["value"]
+    assert d["port_openmp_full_config"]["kind"] == "port" and d["port_openmp_full_config"]["value"] > d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config("cfg1", 1)            # the same dict our arm prints
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -105,9 +105,14 @@ def test_lazy_infos_and_spaces():
     import numpy as np
     from b200bpp.vec_env import LazyInfos, default_item_set, _pack_trajectories
     from b200bpp.spaces import Box, Discrete
-    infos = LazyInfos(np.array([0, 1], bool), np.array([3, 7]), np.array([0.2, 0.5]), 1000.0, 0.0, 100)
-    assert len(infos) == 2 and "episode" not in infos[0] and infos[0]["counter"] == 3
+    # built from the step's 16-byte records: reward bits | placed volume | counter | next action
+    rec = np.array([[0, 200, 3, 17], [0, 500, 7, 4]], np.int32)
+    infos = LazyInfos(np.array([0, 1], bool), rec, 1000.0, 0.0, 100)
+    assert len(infos) == 2 and "episode" not in infos[0] and infos[0]["counter"] == 3 and infos[0]["ratio"] == 0.2
     assert infos[1]["episode"]["r"] == 5.0 and infos[1]["episode"]["l"] == 8 and infos[1]["mask"].shape == (100,)
+    # Monitor rounds the float64 return (baselines/bench/monitor.py:64): exact from the integer volume, for any bin size
+    odd = LazyInfos(np.array([1], bool), np.array([[0, 613, 9, 0]], np.int32), 8 * 12 * 9.0, 0.0, 192)
+    assert odd[0]["episode"]["r"] == round(10.0 * 613 / 864, 6) and odd[0]["ratio"] == 613 / 864
     assert infos.done_indices().tolist() == [1]
     assert len(default_item_set()) == 64 and default_item_set()[1] == (2, 2, 3)
     traj, n = _pack_trajectories([[[2, 3, 4]], [[1, 1, 1], [5, 5, 5]]])
