@@ -278,208 +278,95 @@ __device__ int gen_cut1(const EnvParams &p, GenRng &g, uint32_t *out, Piece *lea
     return n_out;
 }
 
-// cut2, one warp per episode.  The split loop is sequential in the order of the random draws (every lane follows it
-// with the same state; lane 0 writes, the warp shifts the lists), the final stable sort by lz is a ballot compaction
-// per level.  `inv` / `val`: cap + 64 pieces each.
-__device__ int gen_cut2(const EnvParams &p, GenRng &g, uint32_t *out, Piece *inv, Piece *val, int cap, int lane)
+// cut2, one warp per episode.  gen_benchmark's sweep (mdCreator.py:117-135) is sequential in the order of the random
+// draws, so every lane follows it with the same state; lane 0 alone reads and writes the two lists (the current piece
+// reaches the others by shuffle), so the sweep needs no barrier.  What the 32 lanes do share out:
+//   * the draws: 128 at a time, one Philox block per lane, parked in shared memory (a visit takes two);
+//   * invalid_box.remove(box) leaves a tombstone -- within a sweep the elements ahead of the iterator are all live, so
+//     "the iterator skips the element that slid into the vacated slot" is i += 2 -- and the list is compacted between
+//     sweeps with one ballot per 32 entries;
+//   * the stable sort by low_bound (:137-138): one ballot per level and 32 entries.
+// `inv`: cap + 64 pieces; `val`: cap words x | y << 8 | z << 16 | lz << 24; `draws`: 128 words.
+__device__ int gen_cut2(const EnvParams &p, GenRng &g, uint32_t *out, Piece *inv, uint32_t *val, uint32_t *draws, int cap, int lane)
 {
     const int lo = p.lo[0], hi = p.hi[0];
-    int n_inv = 1, n_val = 0;
-    if (lane == 0) inv[0] = mk_piece(p.L, p.W, p.H, 0, 0, 0);
-    __syncwarp();
-    while (n_inv > 0) {                                                   // gen_benchmark, mdCreator.py:117-135
-        int i = 0;
-        while (i < n_inv) {
-            const Piece b = inv[i];
-            const int dim[3] = {px(b), py(b), pz(b)};
-            int fl[3], nf = 0;
-            for (int a = 0; a < 3; ++a) if (dim[a] > hi) fl[nf++] = a;       // benchmark_split, :60-66
-            if (nf == 0) {                                                // unreachable for validated ranges
-                __syncwarp();
-                warp_erase(inv, i, n_inv, lane);
-                --n_inv;
-                if (n_val < cap) { if (lane == 0) val[n_val] = b; ++n_val; }
-                __syncwarp();
-                ++i;
-                continue;
-            }
-            const int ax = fl[__umulhi(g.next(), (uint32_t)nf)];            // :68
-            const int cut = 1 + (int)__umulhi(g.next(), (uint32_t)dim[ax]);   // randint(1, dim)
-            if (cut < lo || dim[ax] - cut < lo) { ++i; continue; }         // rejected, retried in the next sweep
-            Piece p1, p2;
-            if (ax == 0) { p1 = mk_piece(cut, py(b), pz(b), plx(b), ply(b), plz(b)); p2 = mk_piece(px(b) - cut, py(b), pz(b), plx(b) + cut, ply(b), plz(b)); }        // :70-79
-            else if (ax == 1) { p1 = mk_piece(px(b), cut, pz(b), plx(b), ply(b), plz(b)); p2 = mk_piece(px(b), py(b) - cut, pz(b), plx(b), ply(b) + cut, plz(b)); }   // :80-89
-            else { p1 = mk_piece(px(b), py(b), pz(b) - cut, plx(b), ply(b), plz(b)); p2 = mk_piece(px(b), py(b), cut, plx(b), ply(b), plz(b) + pz(b) - cut); }        // :90-99
-            __syncwarp();
-            warp_erase(inv, i, n_inv, lane);                              // invalid_box.remove(box)
-            --n_inv;
-            const Piece sub[2] = {p1, p2};
-            for (int s = 0; s < 2; ++s) {                                 // is_valid, :110-115
-                const Piece q = sub[s];
-                const bool ok = px(q) >= lo && px(q) <= hi && py(q) >= lo && py(q) <= hi && pz(q) >= lo && pz(q) <= hi;
-                if (ok) { if (n_val < cap) { if (lane == 0) val[n_val] = q; ++n_val; } }
-                else if (n_inv < cap + 64) { if (lane == 0) inv[n_inv] = q; ++n_inv; }
-            }
-            __syncwarp();
-            ++i;                                                          // the iterator skips the element that slid into slot i
-        }
-    }
     const unsigned lt = (1u << lane) - 1u;
-    int n_out = 0;                                                        // depart_box: stable sort by low_bound, :137-138
-    for (int level = 0; level <= p.H && n_out < cap; ++level)
-        for (int v0 = 0; v0 < n_val; v0 += 32) {
-            const int v = v0 + lane;
-            const Piece q = v < n_val ? val[v] : 0;
-            const bool hit = v < n_val && plz(q) == level;
-            const unsigned hb = __ballot_sync(kFull, hit);
-            const int pos = n_out + __popc(hb & lt);
-            if (hit && pos < cap) out[pos] = pack_item(px(q), py(q), pz(q));
-            n_out = min(cap, n_out + __popc(hb));
-        }
-    return n_out;
-}
-
-
-// ---------------------------------------------------------------------------------------------------
-// cut2 with one LANE per episode (episodes of up to kLaneVal pieces, i.e. the reference's 10x10x10 configuration).
-// gen_benchmark's sweep (mdCreator.py:117-135) is sequential in the order of the random draws and has no data-parallel
-// part once list removal stops moving memory, so a warp runs 32 independent episodes: every lane keeps its own
-// `invalid_box` list (64-bit pieces) and `valid` list (x | y << 8 | z << 16 | lz << 24) in shared memory, element j of
-// lane l at index j * 32 + l (no bank conflicts while the lanes are in step).  invalid_box.remove(box) leaves a tombstone:
-// within a sweep the elements ahead of the iterator are all live, so "the iterator skips the element that slid into the
-// vacated slot" is simply i += 2; the list is compacted between sweeps.  The stable sort by low_bound (:137-138) is a
-// scan per level.  A lane whose lists would overflow flags its episode; the warp then redoes those with the cooperative
-// version above on the bin's global scratch.
-// ---------------------------------------------------------------------------------------------------
-#ifndef BPP_LANE_INV
-#define BPP_LANE_INV 64
-#endif
-#ifndef BPP_LANE_VAL
-#define BPP_LANE_VAL 128
-#endif
-constexpr int kLaneInv = BPP_LANE_INV, kLaneVal = BPP_LANE_VAL;     // list capacities per lane (tests shrink them to reach the fallback)
-constexpr int kLaneMaxCap = 128;                                    // envs with at most this many pieces per episode take this path
-constexpr int kLaneThreads = 64;
-constexpr size_t kLaneSmemPerWarp = 32 * ((size_t)kLaneInv * 8 + (size_t)kLaneVal * 4);
-
-__device__ __forceinline__ int gen_cut2_lane(const EnvParams &p, GenRng &g, uint32_t *out, int cap, Piece *inv, uint32_t *val,
-                                             int lane, bool &overflow)
-{
-#define BPP_INV(j) inv[(j) * 32 + lane]
-#define BPP_VAL(j) val[(j) * 32 + lane]
-    const int lo = p.lo[0], hi = p.hi[0];
     int n_inv = 1, n_val = 0;
-    BPP_INV(0) = mk_piece(p.L, p.W, p.H, 0, 0, 0);
-    overflow = false;
-    while (n_inv > 0 && !overflow) {                                      // gen_benchmark, mdCreator.py:117-135
+    uint32_t k = 0;                                                       // draws consumed (even)
+    if (lane == 0) inv[0] = mk_piece(p.L, p.W, p.H, 0, 0, 0);
+    while (n_inv > 0) {                                                   // gen_benchmark, mdCreator.py:117-135
         int i = 0, n_phys = n_inv;
         while (i < n_phys) {
-            const Piece b = BPP_INV(i);
+            if ((k & 127u) == 0u) {                                       // next 128 draws of the (domain 2, episode) stream
+                __syncwarp();
+                const uint4 blk = philox4x32_10(make_uint4((k >> 2) + (uint32_t)lane, ((uint32_t)kDomGen << 28) | (g.aux & 0x0FFFFFFFu),
+                                                           (uint32_t)g.gid, (uint32_t)(g.gid >> 32)),
+                                                make_uint2(g.seed_lo, g.seed_hi));
+                reinterpret_cast<uint4 *>(draws)[lane] = blk;
+                __syncwarp();
+            }
+            Piece b = 0;
+            if (lane == 0) b = inv[i];
+            b = __shfl_sync(kFull, b, 0);
             const unsigned fl = (unsigned)(px(b) > hi) | ((unsigned)(py(b) > hi) << 1) | ((unsigned)(pz(b) > hi) << 2);   // benchmark_split, :60-66
-            if (fl == 0u) {                                               // unreachable for validated ranges
-                BPP_INV(i) = 0;
-                if (n_val < kLaneVal) { BPP_VAL(n_val) = pack_item(px(b), py(b), pz(b)) | ((uint32_t)plz(b) << 24); ++n_val; }
-                else overflow = true;
+            if (fl == 0u) {                                               // unreachable for validated ranges (no draw is taken)
+                if (lane == 0) inv[i] = 0;
+                if (n_val < cap) { if (lane == 0) val[n_val] = pack_item(px(b), py(b), pz(b)) | ((uint32_t)plz(b) << 24); ++n_val; }
                 i += 2;
                 continue;
             }
-            const int r = (int)__umulhi(g.next(), (uint32_t)__popc(fl));  // random.choice(flags), :68: the r-th oversize axis
+            const uint32_t u0 = draws[k & 127u], u1 = draws[(k + 1u) & 127u];
+            k += 2u;
+            const int r = (int)__umulhi(u0, (uint32_t)__popc(fl));        // random.choice(flags), :68: the r-th oversize axis
             const unsigned rest = r == 0 ? fl : (r == 1 ? (fl & (fl - 1u)) : 4u);
             const int ax = __ffs(rest) - 1;
             const int side = ax == 0 ? px(b) : (ax == 1 ? py(b) : pz(b));
-            const int cut = 1 + (int)__umulhi(g.next(), (uint32_t)side);  // randint(1, side)
+            const int cut = 1 + (int)__umulhi(u1, (uint32_t)side);        // randint(1, side)
             if (cut < lo || side - cut < lo) { ++i; continue; }            // rejected, retried in the next sweep
             Piece sub[2];
             if (ax == 0) { sub[0] = mk_piece(cut, py(b), pz(b), plx(b), ply(b), plz(b)); sub[1] = mk_piece(px(b) - cut, py(b), pz(b), plx(b) + cut, ply(b), plz(b)); }        // :70-79
             else if (ax == 1) { sub[0] = mk_piece(px(b), cut, pz(b), plx(b), ply(b), plz(b)); sub[1] = mk_piece(px(b), py(b) - cut, pz(b), plx(b), ply(b) + cut, plz(b)); }   // :80-89
             else { sub[0] = mk_piece(px(b), py(b), pz(b) - cut, plx(b), ply(b), plz(b)); sub[1] = mk_piece(px(b), py(b), cut, plx(b), ply(b), plz(b) + pz(b) - cut); }        // :90-99
-            BPP_INV(i) = 0;                                               // invalid_box.remove(box): tombstone
+            if (lane == 0) inv[i] = 0;                                    // invalid_box.remove(box): tombstone
 #pragma unroll
             for (int s = 0; s < 2; ++s) {                                 // is_valid, :110-115
                 const Piece q = sub[s];
                 const bool ok = px(q) >= lo && px(q) <= hi && py(q) >= lo && py(q) <= hi && pz(q) >= lo && pz(q) <= hi;
-                if (ok) {
-                    if (n_val < kLaneVal) { BPP_VAL(n_val) = pack_item(px(q), py(q), pz(q)) | ((uint32_t)plz(q) << 24); ++n_val; }
-                    else overflow = true;
-                } else if (n_phys < kLaneInv) { BPP_INV(n_phys) = q; ++n_phys; }
-                else overflow = true;
+                if (ok) { if (n_val < cap) { if (lane == 0) val[n_val] = pack_item(px(q), py(q), pz(q)) | ((uint32_t)plz(q) << 24); ++n_val; } }
+                else if (n_phys < cap + 64) { if (lane == 0) inv[n_phys] = q; ++n_phys; }
             }
-            if (overflow) break;
             i += 2;                                                       // the iterator skips the element that slid into slot i
         }
-        int k = 0;                                                        // drop the tombstones
-        for (int j = 0; j < n_phys; ++j) {
-            const Piece q = BPP_INV(j);
-            if (q != 0) { BPP_INV(k) = q; ++k; }
+        int keep = 0;                                                     // drop the tombstones, 32 entries per ballot
+        __syncwarp();
+        for (int j0 = 0; j0 < n_phys; j0 += 32) {
+            const int j = j0 + lane;
+            const Piece q = j < n_phys ? inv[j] : 0;
+            const unsigned live = __ballot_sync(kFull, q != 0);
+            __syncwarp();                                                 // every lane has read its entry of this chunk
+            if (q != 0) inv[keep + __popc(live & lt)] = q;
+            keep += __popc(live);
         }
-        n_inv = k;
+        __syncwarp();
+        n_inv = keep;
     }
-    if (overflow) return 0;
+    g.k = k;
+    __syncwarp();
     int n_out = 0;                                                        // depart_box: stable sort by low_bound, :137-138
     for (int level = 0; level <= p.H && n_out < cap; ++level)
-        for (int v = 0; v < n_val && n_out < cap; ++v) {
-            const uint32_t q = BPP_VAL(v);
-            if ((int)(q >> 24) == level) { out[n_out] = q & 0x00ffffffu; ++n_out; }
+        for (int v0 = 0; v0 < n_val; v0 += 32) {
+            const int v = v0 + lane;
+            const uint32_t q = v < n_val ? val[v] : 0u;
+            const bool hit = v < n_val && (int)(q >> 24) == level;
+            const unsigned hb = __ballot_sync(kFull, hit);
+            const int pos = n_out + __popc(hb & lt);
+            if (hit && pos < cap) out[pos] = q & 0x00ffffffu;
+            n_out = min(cap, n_out + __popc(hb));
         }
     return n_out;
-#undef BPP_INV
-#undef BPP_VAL
 }
 
 }  // namespace
-
-// cut2, one lane per episode (see gen_cut2_lane).  mode 0 (init): work item w = bin (w >> 1), buffer / episode e0 + (w & 1);
-// mode 1 (refill): the bins on the refill list get episode sc.episode + 1 into the buffer they are not playing.
-__global__ void __launch_bounds__(kLaneThreads) bpp_gen_cut2_lane_kernel(const EnvParams p, const int mode, const uint32_t e0)
-{
-    BPP_DYNAMIC_SMEM(lane_smem);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Piece *inv = reinterpret_cast<Piece *>(lane_smem + (size_t)warp * kLaneSmemPerWarp);
-    uint32_t *val = reinterpret_cast<uint32_t *>(inv + 32 * kLaneInv);
-    const long long n_work = mode == 0 ? 2ll * p.N : (long long)*p.gen_count;
-    const long long n_threads = (long long)gridDim.x * blockDim.x;
-    // whole warps iterate together (the overflow fallback is warp-cooperative)
-    for (long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; w0 < n_work; w0 += n_threads) {
-        const long long w = w0 + lane;
-        const bool have = w < n_work;
-        long long bin = 0;
-        int buf = 0;
-        uint32_t episode = 0;
-        if (have) {
-            if (mode == 0) { bin = w >> 1; buf = (int)(w & 1); episode = e0 + (uint32_t)buf; }
-            else {
-                bin = (long long)p.gen_list[w];
-                const BinScalars s = p.sc[bin];
-                buf = (int)(s.traj & 1u) ^ 1;
-                episode = s.episode + 1u;
-            }
-        }
-        GenRng g;
-        g.seed_lo = p.seed_lo; g.seed_hi = p.seed_hi; g.aux = episode; g.k = 0; g.blk_idx = 0xffffffffu;
-        g.gid = p.global_offset + (unsigned long long)bin;
-        uint32_t *out = p.ep_items + ((size_t)buf * p.ep_buf_bins + (size_t)bin) * p.ep_cap;
-        bool overflow = false;
-        if (have) {
-            const int n = gen_cut2_lane(p, g, out, p.ep_cap, inv, val, lane, overflow);
-            if (!overflow) p.ep_len2[(size_t)buf * p.ep_buf_bins + (size_t)bin] = n;
-        }
-        unsigned ov = __ballot_sync(kFull, have && overflow);
-        while (ov) {                                                      // lists too long for a lane: the whole warp redoes the episode
-            const int src = __ffs(ov) - 1;
-            ov &= ov - 1;
-            const long long b2 = __shfl_sync(kFull, bin, src);
-            const int buf2 = __shfl_sync(kFull, buf, src);
-            GenRng g2;
-            g2.seed_lo = p.seed_lo; g2.seed_hi = p.seed_hi; g2.aux = __shfl_sync(kFull, episode, src); g2.k = 0; g2.blk_idx = 0xffffffffu;
-            g2.gid = p.global_offset + (unsigned long long)b2;
-            Piece *ginv = reinterpret_cast<Piece *>(p.gen_scratch + (size_t)b2 * (size_t)p.gen_scratch_stride);
-            const int n = gen_cut2(p, g2, p.ep_items + ((size_t)buf2 * p.ep_buf_bins + (size_t)b2) * p.ep_cap, ginv,
-                                   ginv + p.ep_cap + 64, p.ep_cap, lane);
-            if (lane == 0) p.ep_len2[(size_t)buf2 * p.ep_buf_bins + (size_t)b2] = n;
-            __syncwarp();
-        }
-    }
-}
 
 // One warp per episode.  mode 0 (init): every bin gets episode e0 into buffer 0 and e0 + 1 into buffer 1;
 // mode 1 (refill): the bins on the compacted refill list (appended by the step kernel at auto-reset) get episode
@@ -516,8 +403,9 @@ __global__ void __launch_bounds__(128) bpp_gen_kernel(const EnvParams p, const i
                              reinterpret_cast<Piece *>(scratch + o1), p.ep_cap, lane);
             } else {
                 Piece *inv = reinterpret_cast<Piece *>(scratch);
-                Piece *val = inv + p.ep_cap + 64;
-                n = gen_cut2(p, g, out, inv, val, p.ep_cap, lane);
+                uint32_t *val = reinterpret_cast<uint32_t *>(inv + p.ep_cap + 64);
+                uint32_t *draws = val + ((p.ep_cap + 3) & ~3);
+                n = gen_cut2(p, g, out, inv, val, draws, p.ep_cap, lane);
             }
             if (lane == 0) p.ep_len2[(size_t)buf * p.ep_buf_bins + (size_t)bin] = n;
             __syncwarp();
@@ -527,34 +415,17 @@ __global__ void __launch_bounds__(128) bpp_gen_kernel(const EnvParams p, const i
 
 cudaError_t launch_gen(const EnvParams &p, int mode, uint32_t e0, int num_sms, cudaStream_t st)
 {
-    cudaError_t e;
-    if (p.gen_kind == 3 && p.ep_cap <= kLaneMaxCap) {        // cut2 at the reference's bin sizes: one lane per episode
-        const size_t smem = (kLaneThreads / 32) * kLaneSmemPerWarp;
-        static bool opted[64] = {false};
-        int dev = 0;
-        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-        if (!opted[dev & 63]) {
-            e = cudaFuncSetAttribute(bpp_gen_cut2_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            opted[dev & 63] = true;
-        }
-        long long want = ((mode == 0 ? 2ll : 1ll) * p.N + kLaneThreads - 1) / kLaneThreads;
-        const long long cap = (long long)num_sms * 3;     // resident blocks (shared memory: three per SM)
-        if (want > cap) want = cap;
-        BPP_LAUNCH((bpp_gen_cut2_lane_kernel), (unsigned)want, kLaneThreads, smem, st, p, mode, e0);
-    } else {
-        long long want = ((long long)p.N + 3) / 4;        // 4 warps per block, one episode per warp
-        const long long cap = (long long)num_sms * 16;
-        if (mode == 1 && want > cap) want = cap;          // the list length is only known on the device
-        const size_t smem = (size_t)4 * (size_t)p.gen_scratch_stride;
-        const int use_smem = smem <= 200 * 1024;
-        if (use_smem && smem > 48 * 1024) {
-            e = cudaFuncSetAttribute(bpp_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
-        BPP_LAUNCH((bpp_gen_kernel), (unsigned)want, 128, use_smem ? smem : 0, st, p, mode, e0, use_smem);
+    long long want = ((long long)p.N + 3) / 4;            // 4 warps per block, one episode per warp
+    const long long cap = (long long)num_sms * 16;
+    if (mode == 1 && want > cap) want = cap;              // the list length is only known on the device
+    const size_t smem = (size_t)4 * (size_t)p.gen_scratch_stride;
+    const int use_smem = smem <= 200 * 1024;
+    if (use_smem && smem > 48 * 1024) {
+        cudaError_t ea = cudaFuncSetAttribute(bpp_gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ea != cudaSuccess) return ea;
     }
-    e = cudaGetLastError();
+    BPP_LAUNCH((bpp_gen_kernel), (unsigned)want, 128, use_smem ? smem : 0, st, p, mode, e0, use_smem);
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || mode == 0) return e;
     return cudaMemsetAsync(p.gen_count, 0, sizeof(int32_t), st);     // list consumed
 }
@@ -563,7 +434,8 @@ size_t gen_scratch_bytes_per_bin(int gen_kind, int cap)
 {
     if (gen_kind == 2)      // piece list | piece list of the next sweep | meta + candidate lists | shadow heightmap (<= 1024)
         return 2 * (((size_t)cap * sizeof(Piece) + 15) & ~(size_t)15) + (((size_t)cap * 4 + 15) & ~(size_t)15) + 1024;
-    return (((size_t)(cap + 64) * 2 * sizeof(Piece)) + 15) & ~(size_t)15;
+    // cut2: invalid list (cap + 64 pieces) | valid list (cap words) | 128 draws
+    return (size_t)(cap + 64) * sizeof(Piece) + (size_t)((cap + 3) & ~3) * 4 + 512;
 }
 
 }  // namespace bpp

@@ -96,19 +96,3 @@ def test_device_generators_equal_reference_episodes(golden_dir):
                 assert np.array_equal(got, ref_episode(c, b, e)), (c["kind"], c["size"], b, e)
         env.close()
 
-
-def test_cut2_lane_overflow_fallback(golden_dir):
-    """cut2 runs one episode per lane with per-lane lists in shared memory; an episode whose lists would not fit is redone
-    by the whole warp.  Built with tiny lists (4 / 12 entries) almost every episode takes that fallback -- same episodes."""
-    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "simt"))
-    import emul
-    c = [c for c in load_cases(golden_dir) if c["kind"] == "cut2" and c["size"] == (10, 10, 10)][0]
-    nb = 40
-    env = emul.EmulEnv(nb, c["size"], gen="cut2", seed=c["seed"], global_offset=c["gid0"], global_n=1 << 40,
-                       defines=("BPP_LANE_INV=4", "BPP_LANE_VAL=12"))
-    env.reset()
-    for b in range(nb):
-        for e in range(2):
-            w = env.ep_items[e, b, :int(env.ep_len2[e, b])]
-            got = np.stack([w & 0xff, (w >> 8) & 0xff, (w >> 16) & 0xff], 1).astype(np.uint8)
-            assert np.array_equal(got, ref_episode(c, b, e)), (b, e)
