@@ -402,9 +402,11 @@ __global__ void __launch_bounds__(128) bpp_gen_kernel(const EnvParams p, const i
                 n = gen_cut1(p, g, out, leaf, reinterpret_cast<uint16_t *>(scratch + o2), scratch + o3,
                              reinterpret_cast<Piece *>(scratch + o1), p.ep_cap, lane);
             } else {
+                // invalid list | valid list | draws, each 16-byte aligned (the draws are stored 128 bits at a time)
                 Piece *inv = reinterpret_cast<Piece *>(scratch);
-                uint32_t *val = reinterpret_cast<uint32_t *>(inv + p.ep_cap + 64);
-                uint32_t *draws = val + ((p.ep_cap + 3) & ~3);
+                const size_t o1 = ((size_t)(p.ep_cap + 64) * sizeof(Piece) + 15) & ~(size_t)15;
+                uint32_t *val = reinterpret_cast<uint32_t *>(scratch + o1);
+                uint32_t *draws = reinterpret_cast<uint32_t *>(scratch + o1 + (((size_t)p.ep_cap * 4 + 15) & ~(size_t)15));
                 n = gen_cut2(p, g, out, inv, val, draws, p.ep_cap, lane);
             }
             if (lane == 0) p.ep_len2[(size_t)buf * p.ep_buf_bins + (size_t)bin] = n;
@@ -435,7 +437,7 @@ size_t gen_scratch_bytes_per_bin(int gen_kind, int cap)
     if (gen_kind == 2)      // piece list | piece list of the next sweep | meta + candidate lists | shadow heightmap (<= 1024)
         return 2 * (((size_t)cap * sizeof(Piece) + 15) & ~(size_t)15) + (((size_t)cap * 4 + 15) & ~(size_t)15) + 1024;
     // cut2: invalid list (cap + 64 pieces) | valid list (cap words) | 128 draws
-    return (size_t)(cap + 64) * sizeof(Piece) + (size_t)((cap + 3) & ~3) * 4 + 512;
+    return (((size_t)(cap + 64) * sizeof(Piece) + 15) & ~(size_t)15) + (((size_t)cap * 4 + 15) & ~(size_t)15) + 512;
 }
 
 }  // namespace bpp

@@ -165,6 +165,9 @@ __global__ void __launch_bounds__(kThreads, TMA ? tma_min_blocks(ROT, TMA) : BPP
     const long long n_batches = ((long long)p.N + (1 << bpw_log2) - 1) >> bpw_log2;
 #endif
     const int n_steps = FAST ? max(io.n_steps, 1) : 1;
+    // Several env steps per launch on an env small enough that every warp owns at most one batch: its tiles stay in shared
+    // memory from the first step to the last (one bulk load, one bulk store per launch instead of per step).
+    const bool resident = TMA && n_steps > 1 && n_batches <= (long long)gridDim.x * kWarpsPerBlock;
 #pragma unroll 1
     for (int step = 0; step < n_steps; ++step) {
     for (long long batch = (long long)blockIdx.x * kWarpsPerBlock + warp; batch < n_batches;
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, TMA ? tma_min_blocks(ROT, TMA) : BPP
         const long long mybin = have ? bin0 + lane : bin0;
         const unsigned long long gid = p.global_offset + (unsigned long long)mybin;
         uint8_t *hm0 = pinned_ptr(p.hm + (size_t)bin0 * A_pad);
-        if (TMA) {
+        if (TMA && (!resident || step == 0)) {
             // the batch's tiles: one bulk load (the bulk store of this warp's previous batch must have read them out)
             if (lane == 0) {
                 if (n_steps > 1) bulk_wait_all(); else bulk_wait_read<0>();
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, TMA ? tma_min_blocks(ROT, TMA) : BPP
             }
         }
         if (fresh_reset) { s.episode = 0; s.ctr = 0; }
-        if (TMA) {
+        if (TMA && (!resident || step == 0)) {
             __syncwarp();
             mbar_wait_s(sa_bar, tile_phase);
             tile_phase ^= 1u;
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, TMA ? tma_min_blocks(ROT, TMA) : BPP
             // the batch's tiles, updated in place, go back with one bulk store
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && (!resident || step == n_steps - 1)) {
                 bulk_store(hm0, sa_tiles, (uint32_t)(nb * A_pad));
                 bulk_commit();
             }

@@ -41,7 +41,8 @@ def build(defines=(), out=None):
     for old in os.listdir(os.path.dirname(out)):              # earlier builds of this variant
         if old.startswith("libbpp_emul_%s_" % tag[:80]) and old.endswith(".so"):
             os.remove(os.path.join(os.path.dirname(out), old))
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-I", _HERE] + ["-D" + d for d in defines] + \
+    # -fsanitize=alignment: a 128-bit access the GPU would fault on ("misaligned address") aborts here too
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-I", _HERE] + ["-D" + d for d in defines] + \
           ["-o", out + ".tmp", os.path.join(_HERE, "emul_kernels.cpp")]
     env = dict(os.environ)
     env.pop("CC", None)

@@ -523,3 +523,65 @@ def test_headline_shape_every_bin_vs_oracle(env_mod, rot, variant):
     32-bin warp batches): every bin against the oracle at every step, rotation off and on, mask rules v2 and v1."""
     m = run_against_oracle(env_mod, 1 << 19, (10, 10, 10), rot, variant, dict(data_type="rs"), T=6, seed=1234, edge_every=3)
     assert m["steps"] == 6 << 19
+
+
+@pytest.mark.parametrize("n,rot", [(4096, False), (4096, True), (150000, False), (70001, True)])
+def test_packed_results_and_multi_step_launch(env_mod, n, rot):
+    """bpp_step_packed: 16-byte result records instead of four arrays, K env steps in one launch (every step after the
+    first takes the action the previous one sampled).  4096 bins: every warp owns one batch and keeps its tiles in shared
+    memory across the steps; 150 000 bins: 32-bin batches, tiles reloaded every step; 70 001: ragged 16-bin batches."""
+    import torch
+    from b200bpp import _cabi
+    K = 4
+    env = env_mod.BinPackingVecEnv(n, enable_rotation=rot, seed=99, want_sample=True)
+    o = orc.OracleEnv(n, (10, 10, 10), rot=rot, seed=99, n_threads=0)
+    env.reset(); o.reset()
+    lib = _cabi.lib()
+    P = lambda t: C.c_void_p(t.data_ptr())
+    res = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
+    for rnd in range(3):
+        assert np.array_equal(t2n(env.sample_t), o.sample)
+        _cabi.check(lib.bpp_step_packed(env._h, P(env.sample_t), P(env.obs), P(env.location_masks), P(res), P(env.done_t),
+                                        P(env.sample_t), K, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        for _ in range(K):
+            o.step(o.sample.copy())
+        rec = t2n(res)
+        assert np.array_equal(t2n(env.obs), o.obs) and np.array_equal(t2n(env.location_masks), o.mask), rnd
+        assert np.array_equal(rec[:, 0].copy().view(np.float32), o.reward) and np.array_equal(rec[:, 2], o.counter)
+        assert np.array_equal(rec[:, 3].astype(np.int64), o.sample) and np.array_equal(t2n(env.done_t), o.done)
+        assert np.max(np.abs(rec[:, 1] / 1000.0 - o.ratio)) <= 1e-6
+    plain, box, counter, vol = env.export_state()
+    oplain, obox, ocounter, ovol = o.get_state()
+    assert np.array_equal(t2n(plain), oplain) and np.array_equal(t2n(box), obox) and np.array_equal(t2n(vol), ovol)
+    assert env.metrics() == o.metrics()
+    env.close()
+
+
+def test_host_step_views_and_exact_episode_returns(env_mod):
+    """BinPackingVecEnv.step(): reward / done / infos are views of NUMA-local pinned records (valid until the second call
+    after); device and host actions give the same step; info['episode']['r'] is Monitor's round(sum of float64 rewards, 6)
+    for a bin whose volume is not a power of ten."""
+    import torch
+    size = (8, 12, 9)
+    a = env_mod.BinPackingVecEnv(600, size, enable_rotation=True, seed=5, want_sample=True)
+    b = env_mod.BinPackingVecEnv(600, size, enable_rotation=True, seed=5, want_sample=True)
+    o = orc.OracleEnv(600, size, rot=True, seed=5, n_threads=0)
+    a.reset(); b.reset(); o.reset()
+    ret = np.zeros(600)
+    for t in range(30):
+        act = o.sample.copy()
+        _, ra, da, ia = a.step(torch.as_tensor(act, device="cuda").view(-1, 1))      # a GPU policy's actions
+        _, rb, db, ib = b.step(act.reshape(-1, 1))                                   # host actions
+        o.step(act)
+        assert ra.shape == (600, 1) and not ra.is_cuda and da.dtype == np.bool_
+        assert np.array_equal(ra.numpy().reshape(-1), o.reward) and np.array_equal(rb.numpy().reshape(-1), o.reward)
+        assert np.array_equal(da.astype(np.uint8), o.done) and np.array_equal(db.astype(np.uint8), o.done)
+        assert torch.equal(a.obs, b.obs) and torch.equal(a.location_masks, b.location_masks) and torch.equal(a.sample_t, b.sample_t)
+        ret += np.where(o.done == 1, 0.0, o.reward.astype(np.float64))
+        for i in np.flatnonzero(o.done):
+            vol = int(round(float(o.ratio[i]) * 864))
+            assert ia[int(i)]["episode"]["r"] == round(10.0 * vol / 864, 6) and ia[int(i)]["episode"]["l"] == int(o.counter[i]) + 1
+            assert abs(ia[int(i)]["episode"]["r"] - ret[i]) < 5e-6                   # float32 rewards summed vs exact
+            assert ib[int(i)]["ratio"] == vol / 864
+            ret[i] = 0.0
+    a.close(); b.close()

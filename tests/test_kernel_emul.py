@@ -271,9 +271,11 @@ def test_packed_results_and_multi_step_launch(rot, defines):
     """bpp_result records (reward | placed volume | counter | next action) instead of four arrays, and K env steps in ONE
     launch (policy-free rollouts: every step after the first takes the action the previous step sampled) against K single
     steps of the oracle -- on the bulk-copy path (10x10, every output) and with that path compiled out."""
-    N, size, K = 150, (10, 10, 10), 5
-    for gen_kw in (dict(gen="rs"),):
-        e = emul.EmulEnv(N, size, rot=rot, seed=21, defines=defines, **gen_kw)
+    size, K = (10, 10, 10), 5
+    # 150 bins on 16 resident warps: several batches per warp, tiles reloaded every step; 100 bins on 128 warps: every
+    # warp owns at most one batch and keeps its tiles in shared memory across the K steps
+    for N, num_sms, blocks, gen_kw in ((150, 2, 1, dict(gen="rs")), (100, 8, 2, dict(gen="rs"))):
+        e = emul.EmulEnv(N, size, rot=rot, seed=21, defines=defines, num_sms=num_sms, blocks_per_sm=blocks, **gen_kw)
         o = orc.OracleEnv(N, size, rot=rot, seed=21, n_threads=1, **gen_kw)
         e.reset()
         o.reset()
