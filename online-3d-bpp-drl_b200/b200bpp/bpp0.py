@@ -50,9 +50,12 @@ class BoxCreator(object):
 class RandomBoxCreator(BoxCreator):
     """binCreator.py:24-40 (NumPy global RNG, like the reference)"""
 
+    # binCreator.py:25-29: sides 2..6, 125 items (the trainer passes args.box_size_set, sides 2..5, instead)
+    default_box_set = [(2 + i, 2 + j, 2 + k) for i in range(5) for j in range(5) for k in range(5)]
+
     def __init__(self, box_size_set=None):
         super().__init__()
-        self.box_set = box_size_set if box_size_set is not None else default_item_set()
+        self.box_set = box_size_set if box_size_set is not None else RandomBoxCreator.default_box_set
 
     def generate_box_size(self, **kwargs):
         self.box_list.append(tuple(self.box_set[np.random.randint(0, len(self.box_set))]))

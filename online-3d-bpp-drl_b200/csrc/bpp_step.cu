@@ -644,6 +644,24 @@ static cudaError_t launch_t(const EnvParams &p, const StepIO &io, int mode, int 
     EnvParams q = p;
     q.bpw_log2 = TMA ? TMA : 5;
     while (q.bpw_log2 > 0 && (((long long)p.N + (1 << q.bpw_log2) - 1) >> q.bpw_log2) < (cap * kWarpsPerBlock * 4) / 5) --q.bpw_log2;
+    if (q.bpw_log2 < 3) {
+        // Small envs: that rule runs down to one or two bins per warp, where the lane-per-bin phases (about 1.5 bins'
+        // worth of instructions per batch, executed by a whole warp) dominate the instruction volume.  Pick, among the
+        // batch sizes up to 8, the one with the smallest max(instruction volume / issue rate, rounds x latency of one
+        // batch) -- a model with measured constants (profiles/README.md, "Small envs"), not a law.
+        const double i_a = 450.0, i_b = 300.0 * (ROT ? 1.6 : 1.0) * (double)(p.A > 0 ? p.A : 100) / 100.0;
+        const double rate = 0.6 * 4.0 * (double)num_sms, dep = 6.0;      // issued warp-instructions per cycle; cycles per dependent instruction
+        double best = -1.0;
+        int best_log2 = q.bpw_log2;
+        for (int l = q.bpw_log2; l <= 3 && (!TMA || l <= TMA); ++l) {
+            const double nb = (double)(1 << l), batches_l = (double)(((long long)p.N + (1 << l) - 1) >> l);
+            const double rounds = (double)(long long)((batches_l + (double)(cap * kWarpsPerBlock) - 1.0) / (double)(cap * kWarpsPerBlock));
+            const double volume = batches_l * (i_a + nb * i_b) / rate, latency = rounds * (i_a + nb * i_b) * dep;
+            const double t = volume > latency ? volume : latency;
+            if (best < 0.0 || t < best) { best = t; best_log2 = l; }
+        }
+        q.bpw_log2 = best_log2;
+    }
     {   // experiment hook: BPP_BPW_LOG2=k forces 2^k bins per warp batch
         static const char *force = std::getenv("BPP_BPW_LOG2");
         if (force && force[0] >= '0' && force[0] <= '5') q.bpw_log2 = force[0] - '0';
