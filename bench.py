@@ -10,7 +10,7 @@ heightmap update, reward/done/info, auto-reset, next item, float32 observation, 
 mask, and the next uniformly-random valid action (the policy stand-in, fused into the same launch).
 
   value      env-steps/s with all inputs resident in HBM (CUDA events around K steps, max over ranks)
-  e2e        the same through the C ABI with HOST buffers (bpp_step_packed_host): every step the int64 actions are read
+  e2e        the same through the C ABI with HOST buffers (bpp_step_packed_host_i32): every step the int32 actions are read
              from pinned host memory and one 16-byte result record + one done byte per bin are written to pinned host
              memory (what VecPyTorch.step_async / step_wait move, acktr/envs.py:182-193); obs and mask stay on the
              device as in the reference.  e2e_py is the public Python call, BinPackingVecEnv.step(), timed the same way.
@@ -290,24 +290,24 @@ class Runner(object):
 
 
 def time_e2e(r, steps, warmup=3):
-    """(ms per step, wall ms per step) through bpp_step_packed_host with NUMA-local pinned buffers."""
+    """(wall ms per step, done fraction) through the C ABI with NUMA-local pinned HOST buffers, stream synchronised every
+    step.  Every step the kernel reads its int32 actions from pinned host memory -- the next_action column of the records
+    the previous step wrote there: the policy stand-in's output, handed back without a host pass -- and writes one 16-byte
+    record + one done byte per bin to pinned host memory."""
     import torch
     from b200bpp.vec_env import _HostBuffer
     lib, N, dev = r.lib, r.N, r.dev
-    hb = [_HostBuffer(lib, dev.index, 8 * N), _HostBuffer(lib, dev.index, 8 * N), _HostBuffer(lib, dev.index, 16 * N),
-          _HostBuffer(lib, dev.index, N)]
-    act = [torch.from_numpy(h.view(np.int64, (N,))) for h in hb[:2]]
-    act[0].copy_(r.bufs[r.k & 1].cpu())
+    hb = [_HostBuffer(lib, dev.index, 16 * N), _HostBuffer(lib, dev.index, 16 * N), _HostBuffer(lib, dev.index, N)]
+    rec = [h.view(np.int32, (N, 4)) for h in hb[:2]]
+    rec[0][:, 3] = r.bufs[r.k & 1].cpu().numpy().astype(np.int32)      # the env's pending sampled actions
     torch.cuda.synchronize(dev)
     k = 0
 
     def step():
         nonlocal k
-        # the policy stand-in's output becomes the next step's input without a host pass: the kernel writes the next
-        # sampled action as int64 straight into the other pinned action buffer (`sample` may be pinned host memory)
-        r._cabi.check(lib.bpp_step_packed_host(r.env._h, C.c_void_p(hb[k & 1].ptr), r.P(r.env.obs), r.P(r.env.location_masks),
-                                               C.c_void_p(hb[2].ptr), C.c_void_p(hb[3].ptr), C.c_void_p(hb[(k + 1) & 1].ptr),
-                                               C.c_void_p(r.stream.cuda_stream)))
+        src, dst = hb[k & 1], hb[(k + 1) & 1]
+        r._cabi.check(lib.bpp_step_packed_host_i32(r.env._h, C.c_void_p(src.ptr + 12), 4, r.P(r.env.obs), r.P(r.env.location_masks),
+                                                   C.c_void_p(dst.ptr), C.c_void_p(hb[2].ptr), None, C.c_void_p(r.stream.cuda_stream)))
         k += 1
     for _ in range(warmup):
         step()
@@ -317,9 +317,9 @@ def time_e2e(r, steps, warmup=3):
         step()
     torch.cuda.synchronize(dev)
     wall = 1e3 * (time.perf_counter() - t0) / steps
-    done_frac = float(hb[3].view(np.uint8, (N,)).mean())
+    done_frac = float(hb[2].view(np.uint8, (N,)).mean())
     # leave the device-side action buffer in step with the env
-    r.bufs[r.k & 1].copy_(act[k & 1])
+    r.bufs[r.k & 1].copy_(torch.from_numpy(rec[k & 1][:, 3].astype(np.int64)))
     torch.cuda.synchronize(dev)
     for h in hb:
         h.free()
@@ -470,13 +470,12 @@ def main():
             "config": workload_config(args.workload, world, args.bins_per_gpu),
             "build": r.lib.bpp_build_info().decode(),
             "e2e": {"value": total_bins / (e2e_ms * 1e-3), "unit": "env-steps/s", "steps": e2e_steps,
-                    "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 25 * N, "ms_per_step": e2e_ms,
-                    "api": "bpp_step_packed_host (the call under BinPackingVecEnv.step): int64 actions read from pinned, "
-                           "NUMA-local host memory, one 16-byte result record (reward, placed volume, counter, next "
-                           "action) + one done byte per bin written to pinned host memory, zero-copy over PCIe inside the "
-                           "kernel, stream synchronised every step; the policy stand-in's next action returns as int64 into the other "
-                           "pinned action buffer (8 more bytes per bin); obs+mask stay on "
-                           "the device as in acktr/envs.py:191; wall clock, max over ranks"},
+                    "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": 17 * N, "ms_per_step": e2e_ms,
+                    "api": "bpp_step_packed_host_i32 (bpp_step_packed_host, the call under BinPackingVecEnv.step, with int32 "
+                           "actions): actions read from pinned, NUMA-local host memory (the next_action column of the previous "
+                           "step's records), one 16-byte result record (reward, placed volume, counter, next action) + one done "
+                           "byte per bin written to pinned host memory, zero-copy over PCIe inside the kernel, stream "
+                           "synchronised every step; obs+mask stay on the device as in acktr/envs.py:191; wall clock, max over ranks"},
             "e2e_py": {"value": total_bins / (e2e_py_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": e2e_py_ms,
                        "api": "obs, reward, done, infos = BinPackingVecEnv.step(actions) with the actions a GPU policy hands "
                               "over (device int64[N,1]); reward float32[N,1], done np.bool_[N] and the lazy infos are views "

@@ -140,6 +140,12 @@ int32_t bpp_step_packed(bpp_env *env, const int64_t *actions, float *obs, float 
 int32_t bpp_step_packed_host(bpp_env *env, const int64_t *actions_host, float *obs, float *mask,
                              bpp_result *results_host, uint8_t *done_host, int64_t *sample, void *stream);
 
+/* The same with int32 actions read with a stride (in int32 units): half the bytes on the wire, and
+ * (actions_host = &results_prev[0].next_action, stride = 4) takes a policy-free rollout's actions straight out of the
+ * records of the previous step.  actions / results / done must be pinned mapped host memory or device memory. */
+int32_t bpp_step_packed_host_i32(bpp_env *env, const int32_t *actions_host, int32_t stride, float *obs, float *mask,
+                                 bpp_result *results_host, uint8_t *done_host, int64_t *sample, void *stream);
+
 /* -- pinned, device-mapped host memory placed on the NUMA node of `device` (the calling thread is bound to that node's
  *    CPUs while the pages are allocated and touched, then gets its affinity back), and a helper that binds the calling
  *    thread there for good -- what a per-GPU rollout worker should do before it starts launching. */

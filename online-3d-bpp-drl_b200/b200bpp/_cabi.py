@@ -49,6 +49,7 @@ SYMBOLS = {
     "bpp_step_host": (_i32, [_vp] * 10),
     "bpp_step_packed": (_i32, [_vp] * 7 + [_i32, _vp]),
     "bpp_step_packed_host": (_i32, [_vp] * 8),
+    "bpp_step_packed_host_i32": (_i32, [_vp, _vp, _i32] + [_vp] * 6),
     "bpp_host_alloc": (_i32, [_i32, C.c_uint64, C.POINTER(_vp)]),
     "bpp_host_free": (_i32, [_vp]),
     "bpp_bind_thread_to_device": (_i32, [_i32]),

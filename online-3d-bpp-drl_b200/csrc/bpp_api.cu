@@ -275,6 +275,7 @@ static int run_step_range(bpp_env *env, const StepIO &io_all, int mode, long lon
     p.global_offset += (unsigned long long)b0;
     p.ep_bin0 = b0;
     if (io.actions) io.actions += b0;
+    if (io.actions32) io.actions32 += (size_t)b0 * (size_t)io.actions32_stride;
     if (io.obs) io.obs += (size_t)b0 * 4 * p.A;
     if (io.mask) io.mask += (size_t)b0 * p.M;
     if (io.reward) io.reward += b0;
@@ -490,6 +491,37 @@ int32_t bpp_step_packed_host(bpp_env *env, const int64_t *actions_host, float *o
         BPP_CUDA(cudaMemcpyAsync(done_host, env->d_done, N, cudaMemcpyDeviceToHost, st));
     }
     env->steps += (unsigned long long)N;
+    BPP_CUDA(cudaStreamSynchronize(st));
+    return BPP_OK;
+}
+
+
+int32_t bpp_step_packed_host_i32(bpp_env *env, const int32_t *actions_host, int32_t stride, float *obs, float *mask,
+                                 bpp_result *results_host, uint8_t *done_host, int64_t *sample, void *stream)
+{
+    if (int rc = enter(env, "bpp_step_packed_host_i32")) return rc;
+    if (!env->was_reset) return fail(BPP_ERR_STATE, "bpp_step_packed_host_i32: call bpp_reset first");
+    if (!actions_host || !results_host || !done_host || !obs || !mask || stride < 1)
+        return fail(BPP_ERR_INVALID, "bpp_step_packed_host_i32: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    StepIO io{};
+    io.obs = obs; io.mask = mask; io.n_steps = 1;
+    io.sample = reinterpret_cast<long long *>(sample);
+    const void *hosts[5] = {actions_host, results_host, nullptr, done_host, nullptr};
+    if (!zero_copy_aliases(env, hosts) || !aligned16(env->zc_dev[1]))
+        return fail(BPP_ERR_INVALID, "bpp_step_packed_host_i32: actions, results and done must be pinned mapped host memory "
+                                     "(bpp_host_alloc) or device memory");
+    io.actions32 = static_cast<const int32_t *>(env->zc_dev[0]);
+    io.actions32_stride = stride;
+    io.actions = reinterpret_cast<const long long *>(io.actions32);     // non-null marker for the launch code; never read
+    io.packed = static_cast<uint4 *>(env->zc_dev[1]);
+    io.done = static_cast<uint8_t *>(env->zc_dev[3]);
+    if (int rc = run_step(env, io, kModeStep, stream)) return rc;
+    if (env->p.gen_kind >= 2) {
+        BPP_CUDA(launch_gen(env->p, 1, 0u, env->num_sms, st));
+        g_launches.fetch_add(1);
+    }
+    env->steps += (unsigned long long)env->p.N;
     BPP_CUDA(cudaStreamSynchronize(st));
     return BPP_OK;
 }

@@ -175,6 +175,10 @@ struct StepIO {
     // next sampled action i32): one 128-bit store per bin instead of reward / counter / ratio / sample; `done` stays a
     // separate byte array (the host reads it as np.bool_ without a pass over the records).
     uint4 *packed;              // [N] or null
+    // actions as int32 with a stride (in int32 units) instead of `actions`: half the bytes on the wire, and stride 4 /
+    // offset 3 reads them straight out of the previous step's records (policy-free rollouts through host memory)
+    const int32_t *actions32;
+    int actions32_stride;
     int n_steps;                // >= 1: env steps per launch; steps after the first take the previous step's sampled
                                 // action (policy-free rollouts; rs / replay only, needs `sample` or `packed`)
 };

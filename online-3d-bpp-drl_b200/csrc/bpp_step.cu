@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, TMA ? tma_min_blocks(ROT, TMA) : BPP
             s.box = a.x; s.cnt = (int)a.y; s.vol = (int)a.z; s.episode = a.w;
             s.ctr = b.x; s.pos = (int)b.y; s.ep_len = (int)b.z; s.traj = b.w;
             if (mode == kModeStep) {
-                if (step == 0) action = io.actions[mybin];
+                if (step == 0) action = io.actions32 ? (long long)io.actions32[(size_t)mybin * (size_t)io.actions32_stride] : io.actions[mybin];
                 else action = io.sample ? io.sample[mybin] : (long long)(int)io.packed[mybin].w;   // written by this lane one step ago
             }
         }

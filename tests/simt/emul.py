@@ -59,7 +59,7 @@ class _Buffers(C.Structure):
 
 class _IO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("actions", "obs", "mask", "reward", "done", "counter", "ratio", "sample", "packed")] + \
-               [("n_steps", C.c_int32)]
+               [("n_steps", C.c_int32), ("actions32", C.c_void_p), ("actions32_stride", C.c_int32)]
 
 
 _libs = {}
@@ -182,11 +182,13 @@ class EmulEnv(object):
         self.steps = 0
 
     def _call(self, mode, actions=None, want_obs=True, want_mask=True, want_sample=True, scalars=True, packed=False,
-              n_steps=1):
+              n_steps=1, actions32=None, actions32_stride=1):
         """packed: results as 16-byte records (self.packed: reward f32 | vol i32 | counter i32 | next action i32) instead of
         reward / counter / ratio / sample; n_steps: env steps in one launch (later steps take the sampled action)."""
         io = _IO()
         io.n_steps = int(n_steps)
+        if actions32 is not None:       # int32 actions with a stride (e.g. the next_action column of the previous records)
+            io.actions32, io.actions32_stride = actions32.ctypes.data, int(actions32_stride)
         if packed and mode == 0:
             if getattr(self, "packed", None) is None:
                 self.packed = _aligned((self.N, 4), np.int32)

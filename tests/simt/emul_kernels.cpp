@@ -43,6 +43,8 @@ struct EmulIO {
     int64_t *sample;
     void *packed;                // bpp_result[N] (16 B) or null
     int32_t n_steps;             // env steps per launch (0 / 1 = one)
+    const int32_t *actions32;    // int32 actions with a stride, instead of `actions`
+    int32_t actions32_stride;
 };
 
 static EnvParams make_params(const bpp_config *cfg, const EmulBuffers *b)
@@ -81,6 +83,7 @@ int emul_env_call(const bpp_config *cfg, const EmulBuffers *b, const EmulIO *io_
     io.counter = io_in->counter; io.ratio = io_in->ratio; io.sample = reinterpret_cast<long long *>(io_in->sample);
     io.packed = static_cast<uint4 *>(io_in->packed);
     io.n_steps = io_in->n_steps > 1 ? io_in->n_steps : 1;
+    io.actions32 = io_in->actions32; io.actions32_stride = io_in->actions32_stride;
     io.episode_inc = (mode == kModeReset && was_reset) ? 1 : 0;
     const bool cut = p.gen_kind >= 2;
     const int rot = cfg->rot ? 1 : 0;

@@ -585,3 +585,35 @@ def test_host_step_views_and_exact_episode_returns(env_mod):
             assert ib[int(i)]["ratio"] == vol / 864
             ret[i] = 0.0
     a.close(); b.close()
+
+
+def test_int32_strided_actions_from_previous_records(env_mod):
+    """bpp_step_packed_host_i32: int32 actions read with a stride from pinned host memory -- here the next_action column
+    of the records the previous step wrote -- give the same rollout as int64 actions through bpp_step_packed_host."""
+    import torch
+    from b200bpp import _cabi
+    from b200bpp.vec_env import _HostBuffer
+    n = 3000
+    a = env_mod.BinPackingVecEnv(n, enable_rotation=True, seed=8, want_sample=True)
+    b = env_mod.BinPackingVecEnv(n, enable_rotation=True, seed=8, want_sample=True)
+    a.reset(); b.reset()
+    lib = _cabi.lib()
+    P = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    hb = [_HostBuffer(lib, 0, 16 * n), _HostBuffer(lib, 0, 16 * n), _HostBuffer(lib, 0, n), _HostBuffer(lib, 0, 8 * n),
+          _HostBuffer(lib, 0, 16 * n), _HostBuffer(lib, 0, n)]
+    rec = [h.view(np.int32, (n, 4)) for h in hb[:2]]
+    rec[0][:, 3] = t2n(a.sample_t).astype(np.int32)
+    act64, rec_b, done_b = hb[3].view(np.int64, (n,)), hb[4].view(np.int32, (n, 4)), hb[5].view(np.uint8, (n,))
+    for t in range(12):
+        act64[:] = rec[t & 1][:, 3]
+        _cabi.check(lib.bpp_step_packed_host_i32(a._h, C.c_void_p(hb[t & 1].ptr + 12), 4, P(a.obs), P(a.location_masks),
+                                                 C.c_void_p(hb[(t + 1) & 1].ptr), C.c_void_p(hb[2].ptr), None, st))
+        _cabi.check(lib.bpp_step_packed_host(b._h, C.c_void_p(hb[3].ptr), P(b.obs), P(b.location_masks), C.c_void_p(hb[4].ptr),
+                                             C.c_void_p(hb[5].ptr), None, st))
+        assert np.array_equal(rec[(t + 1) & 1], rec_b) and np.array_equal(hb[2].view(np.uint8, (n,)), done_b)
+        assert torch.equal(a.obs, b.obs) and torch.equal(a.location_masks, b.location_masks)
+    assert a.metrics() == b.metrics() and a.metrics()["episodes"] > 0
+    a.close(); b.close()
+    for h in hb:
+        h.free()

@@ -292,6 +292,12 @@ def test_packed_results_and_multi_step_launch(rot, defines):
             vol = rec[:, 1].astype(np.float64) / 1000.0
             assert np.max(np.abs(vol - o.ratio)) <= 1e-6
             assert np.array_equal(e.sample, o.sample)          # `sample` is still written next to the records
+        # int32 actions with a stride: the next_action column of the last records drives one more step
+        prev = e.packed.copy()
+        e._call(0, None, packed=True, actions32=prev[:, 3], actions32_stride=4)
+        o.step(o.sample.copy())
+        assert np.array_equal(e.obs, o.obs) and np.array_equal(e.mask, o.mask)
+        assert np.array_equal(e.packed[:, 0].view(np.float32), o.reward) and np.array_equal(e.done, o.done)
         for a, b in zip(e.get_state(), o.get_state()):
             assert np.array_equal(a, b)
         m = e.metrics_dict()
