@@ -102,6 +102,37 @@ __global__ void __launch_bounds__(kThreads, 4) k_bulk(float *out, int n_bins, in
     if (lane == 0) bulk_wait_read<0>();
 }
 
+
+// (e) the same rows, but every warp owns BATCHES of `bpb` consecutive bins which it writes one after the other (the step
+// kernel's assignment: neighbouring warps are bpb bins = bpb * 2000 bytes apart), by five bulk stores per bin
+__global__ void __launch_bounds__(kThreads, 4) k_bulk_batched(float *out, int n_bins, int bpb)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 *lut = reinterpret_cast<float4 *>(smem);
+    for (int k = threadIdx.x; k < 8 * kBinBytes / 16; k += kThreads) {
+        const float v = (float)(k / (kBinBytes / 16));
+        lut[k] = make_float4(v, v, v, v);
+    }
+    __syncthreads();
+    fence_async_smem();
+    const long long n_batches = n_bins / bpb;
+    for (long long batch = (long long)blockIdx.x * kWarps + warp; batch < n_batches; batch += (long long)gridDim.x * kWarps) {
+        for (int j = 0; j < bpb; ++j) {
+            const long long b = batch * bpb + j;
+            uint8_t *o = reinterpret_cast<uint8_t *>(out) + b * kBinBytes;
+            const uint8_t *src = smem + (b & 7) * kBinBytes;
+            if (lane == 0) {
+                for (int r = 0; r < kRowsPerBin; ++r) bulk_store(o + r * kRow, src + r * kRow, kRow);
+                bulk_commit();
+                bulk_wait_read<8>();
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) bulk_wait_read<0>();
+}
+
 // tile loads: 112-byte u8 tiles.  MODE 0: per bin, lanes 0..6 LDG.128 -> STS.128 (round-1 kernel, prefetch one ahead);
 // MODE 1: one bulk load of 32 tiles (3 584 B) per batch + mbarrier, double-buffered.  The warp sums the bytes.
 template <int MODE>
@@ -197,6 +228,11 @@ int main()
         ms = time_ms([&] { k_bulk<1><<<grid, kThreads, smem_bulk>>>(out, n_bins, 1, staged); });
         printf("{\"exp\": \"bulk_store_staged%d_rows_sts_then_%d_copies\", \"ms\": %.4f, \"GBps\": %.0f}\n", staged,
                (staged > 0) + 5 - staged, ms, gb / (ms * 1e-3));
+    }
+    CK(cudaFuncSetAttribute(k_bulk_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bulk));
+    for (int g : {3, 4}) for (int bpb : {1, 16, 32}) {
+        ms = time_ms([&] { k_bulk_batched<<<prop.multiProcessorCount * g, kThreads, smem_bulk>>>(out, n_bins, bpb); });
+        printf("{\"exp\": \"bulk_store_5x400B_batches_of_%d_bins_per_warp_%d_ctas_per_sm\", \"ms\": %.4f, \"GBps\": %.0f}\n", bpb, g, ms, gb / (ms * 1e-3));
     }
     const double gbt = (double)n_bins * 112 / 1e9;
     ms = time_ms([&] { k_tiles<0><<<grid, kThreads, kWarps * 2 * 3584>>>(hm, sink, n_bins); });
