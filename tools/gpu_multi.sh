@@ -4,7 +4,7 @@ cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}" || exit 1
 mkdir -p gpurun_out
 G=$(nvidia-smi -L | wc -l)
 nvidia-smi topo -m > gpurun_out/topo_$G.txt 2>&1
-for n in 1 2 4 8; do
+for n in ${NLIST:-1 2 4 8}; do
   [ $n -le $G ] || break
   if [ $n = 1 ]; then
     timeout 300 python bench.py --gpus 1 --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/multi_n$n.json 2> gpurun_out/multi_n$n.err
