@@ -24,10 +24,6 @@ VARIANTS = {
     "nouni": ["BPP_UNIFORM=0"],                   # ordinary instantiations without the uniform-datapath trick
     # bulk-copy path: bins per warp batch x resident CTAs per SM
     "n16": ["BPP_TMA_BPW_LOG2=4"],
-    # shared memory is the busiest unit of the bulk-copy kernel (36 % of its wavefronts are bank conflicts of the pair loads)
-    "split": ["BPP_PAIRS_SPLIT=1"],
-    "words": ["BPP_LANE_CHECK_WORDS=1"],
-    "split_words": ["BPP_PAIRS_SPLIT=1", "BPP_LANE_CHECK_WORDS=1"],
 }
 
 

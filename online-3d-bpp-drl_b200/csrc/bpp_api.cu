@@ -109,7 +109,7 @@ uint64_t bpp_launch_count(void) { return g_launches.load(); }
 const char *bpp_build_info(void)
 {
     return "packed_sweep=" BPP_STR(BPP_PACKED_SWEEP) " lane_check=" BPP_STR(BPP_LANE_CHECK) " square_copy=" BPP_STR(BPP_SQUARE_COPY)
-           " plain_stores=" BPP_STR(BPP_PLAIN_STORES) " pairs_split=" BPP_STR(BPP_PAIRS_SPLIT) " tma=" BPP_STR(BPP_TMA)
+           " plain_stores=" BPP_STR(BPP_PLAIN_STORES) " tma=" BPP_STR(BPP_TMA)
            " tma_bpw_log2=" BPP_STR(BPP_TMA_BPW_LOG2) "/" BPP_STR(BPP_TMA_BPW_LOG2_ROT)
            " warps_per_block=" BPP_STR(BPP_WARPS_PER_BLOCK) " sm_100a";
 }

@@ -35,28 +35,6 @@ constexpr unsigned kFull = 0xffffffffu;
 #define BPP_PACKED_SWEEP 1
 #endif
 constexpr bool kPackedSweep = BPP_PACKED_SWEEP != 0;
-// Build switch (off until measured): the pair words of even and odd cells live in two separate halves of the pairs
-// array.  A lane's pair of positions starts at an even cell, so for a given window cell all lanes of a load read
-// cells of one parity: interleaved, they fall on every other bank (3-way conflicts at 10x10, ncu: 7.5 M conflicts per
-// launch); split, on consecutive banks.
-// Build switch (on = round-1 behaviour): the constant x / y / z planes of the observation come from a shared-memory
-// table of (v, v, v, v) rows -- three broadcast LDS.128 per bin, 6 shared-memory wavefronts -- instead of three
-// int-to-float conversions.  Saves issue slots, costs load/store-unit bandwidth; 0 = convert in registers.
-#ifndef BPP_PLANE_LUT
-#define BPP_PLANE_LUT 1
-#endif
-constexpr bool kPlaneLut = BPP_PLANE_LUT != 0;
-// Build switch (off until measured): two batch sizes per launch.  16 384 batches of 32 bins over 4 736 resident warps
-// are 3.46 batches per warp, i.e. 4 rounds for some warps and 3 for the others; with the switch the launch runs whole
-// rounds of 2^bpw_log2-bin batches and then ONE round of smaller batches that every warp takes part in
-// (choose_batches() in bpp_params.h).
-#ifndef BPP_TWO_TIER
-#define BPP_TWO_TIER 0
-#endif
-#ifndef BPP_PAIRS_SPLIT
-#define BPP_PAIRS_SPLIT 0
-#endif
-constexpr bool kPairsSplit = BPP_PAIRS_SPLIT != 0;
 // Build switch (on by default): the placement check of step() (Space.check_box at the chosen position) runs in the lane-per-bin phase
 // straight from the heightmap in global memory for footprints of up to 32 cells; the warp-per-bin phase then only
 // raises the footprint.  Larger footprints (the (10,10,10) sentinels) keep the warp-cooperative check.
@@ -131,10 +109,6 @@ enum Mode : int { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
 struct EnvParams {
     int N, L, W, H, A, A_pad, M, M_pad;      // M = A * (1 + rot): mask length
     int bpw_log2;                            // log2(bins per warp batch), chosen per launch
-#if BPP_TWO_TIER
-    long long n_full;                        // batches of 2^bpw_log2 bins (whole rounds over the resident warps) ...
-    int tail_log2;                           // ... followed by one round of batches of 2^tail_log2 bins
-#endif
     int gen_kind;
     int n_items;
     const uint32_t *item_set;                // packed x | y<<8 | z<<16
@@ -436,39 +410,6 @@ __device__ __forceinline__ void window_stats_rows5(const T *w, int W, int x, int
     }
 }
 
-// Same again, with the 5 cells of a row taken from the two aligned 32-bit words that contain them (2 global loads per
-// row instead of 5 byte loads: the lane-per-bin check costs load/store-unit requests, 32 different sectors per
-// instruction).  Reads up to 7 bytes past the row's first cell.  Build switch BPP_LANE_CHECK_WORDS (off until measured).
-#ifndef BPP_LANE_CHECK_WORDS
-#define BPP_LANE_CHECK_WORDS 0
-#endif
-constexpr bool kLaneCheckWords = BPP_LANE_CHECK_WORDS != 0;
-__device__ __forceinline__ void window_stats_rows5_words(const uint8_t *w, int W, int x, int y, int &m, int &cnt)
-{
-    m = -1;
-    cnt = 0;
-#pragma unroll 1
-    for (int r = 0; r < x; ++r) {
-        const uint8_t *row = w + r * W;
-        const uint32_t sh = ((uint32_t)(uintptr_t)row & 3u) * 8u;
-        const uint32_t *aw = reinterpret_cast<const uint32_t *>(row - (sh >> 3));
-        const uint32_t w0 = aw[0], w1 = aw[1];
-        const uint32_t lo = __funnelshift_r(w0, w1, sh);          // cells 0..3 of the row
-        int h[5];
-        h[0] = (int)(lo & 0xffu); h[1] = (int)((lo >> 8) & 0xffu); h[2] = (int)((lo >> 16) & 0xffu); h[3] = (int)(lo >> 24);
-        h[4] = (int)((w1 >> sh) & 0xffu);
-#pragma unroll
-        for (int c = 0; c < 5; ++c) h[c] = c < y ? h[c] : -1;
-        const int rm = max(max(max(h[0], h[1]), max(h[2], h[3])), h[4]);
-        int below = 0;
-#pragma unroll
-        for (int c = 0; c < 5; ++c) below += min(rm - h[c], 1);
-        const int rc = 5 - below;
-        cnt = rm > m ? rc : cnt + (rm == m ? rc : 0);
-        m = max(m, rm);
-    }
-}
-
 // Same for a compile-time footprint: all cells go to registers, max tree, then the cells below the max are
 // counted with min(m - h, 1); the four corners come out of the same registers.
 template <int X, int Y>
@@ -584,21 +525,11 @@ __device__ __forceinline__ int sweep_loop_packed(const uint32_t *pairs, uint8_t 
             const int i = (int)(((uint32_t)u * kRcp) >> 16), jp = u - i * kNpj;
             const int idx = i * CS + 2 * jp;
             uint32_t g[a];
-            if (kPairsSplit) {
-                // cell idx + d sits in half (d & 1) at word (idx >> 1) + (d >> 1); idx is even
-                constexpr int kHalf = ((CS * CS + 15) & ~15) / 2;
-                const uint32_t *w = pairs + (idx >> 1);
+            const uint32_t *w = pairs + idx;
 #pragma unroll
-                for (int r = 0; r < X; ++r)
+            for (int r = 0; r < X; ++r)
 #pragma unroll
-                    for (int c = 0; c < Y; ++c) g[r * Y + c] = w[((r * CS + c) & 1) * kHalf + ((r * CS + c) >> 1)];
-            } else {
-                const uint32_t *w = pairs + idx;
-#pragma unroll
-                for (int r = 0; r < X; ++r)
-#pragma unroll
-                    for (int c = 0; c < Y; ++c) g[r * Y + c] = w[r * CS + c];
-            }
+                for (int c = 0; c < Y; ++c) g[r * Y + c] = w[r * CS + c];
             uint32_t gm = g[0];
 #pragma unroll
             for (int k = 1; k + 1 < a; k += 2) gm = __vimin3_u16x2(gm, g[k], g[k + 1]);
@@ -636,14 +567,7 @@ __device__ __forceinline__ void build_pairs(const uint8_t *tile, uint32_t *pairs
         o.y = 0x00ff00ffu - __byte_perm(w0, 0u, 0x4241);
         o.z = 0x00ff00ffu - __byte_perm(w0, 0u, 0x4342);
         o.w = 0x00ff00ffu - __byte_perm(__funnelshift_r(w0, w1, 24), 0u, 0x4140);   // last byte of w0, first of w1
-        if (kPairsSplit) {        // cells 4k, 4k+2 -> even half words 2k, 2k+1; cells 4k+1, 4k+3 -> odd half
-            const int half = ((A + 15) & ~15) >> 1;
-            uint2 *e2 = reinterpret_cast<uint2 *>(pairs), *o2 = reinterpret_cast<uint2 *>(pairs + half);
-            e2[k] = make_uint2(o.x, o.z);
-            o2[k] = make_uint2(o.y, o.w);
-        } else {
-            p4[k] = o;
-        }
+        p4[k] = o;
     }
 }
 

@@ -47,32 +47,6 @@ inline void derive_params(const bpp_config &cfg, EnvParams &p)
     }
 }
 
-// Two-tier batching (BPP_TWO_TIER): `rounds` whole rounds of 2^full_log2-bin batches over `warps` resident warps, then
-// one round of 2^tail_log2-bin batches for what is left.  Chosen to minimise rounds * (2^full_log2 + c) + (2^tail_log2 + c)
-// bins' worth of time per warp, c = the lane-per-bin phases of a batch counted as 2 bins.  n_full = rounds * warps.
-struct BatchPlan {
-    int full_log2, tail_log2;
-    long long n_full, n_tail;
-};
-inline BatchPlan choose_batches(long long N, long long warps)
-{
-    BatchPlan best{5, 0, 0, 0};
-    long long best_cost = -1;
-    for (int fl = 5; fl >= 0; --fl) {
-        const long long per_round = warps << fl;
-        const long long rounds = N / per_round, rest = N - rounds * per_round;
-        int tl = 0;
-        while (((long long)warps << tl) < rest) ++tl;          // smallest batch that covers the rest in one round
-        if (tl > fl) continue;                                 // (rest < per_round, so this cannot happen; kept as a guard)
-        const long long cost = rounds * ((1ll << fl) + 2) + (rest > 0 ? (1ll << tl) + 2 : 0);
-        if (best_cost < 0 || cost < best_cost) {
-            best_cost = cost;
-            best = BatchPlan{fl, tl, rounds * warps, rest > 0 ? (rest + (1ll << tl) - 1) >> tl : 0};
-        }
-    }
-    return best;
-}
-
 // Dynamic shared memory of one step-kernel CTA.  Ordinary path: per warp the heightmap tile, the mask tile, the packed
 // sweep's pair array (compile-time bin sides only) and 32 staged bin records.  Bulk-copy path (tma): the table of
 // constant observation planes, then per warp the batch's tiles, mask tile, pairs, float32 staging rows and records.

@@ -158,12 +158,7 @@ __global__ void __launch_bounds__(kThreads, TMA ? tma_min_blocks(ROT, TMA) : BPP
     // bins per warp batch: 32 when there are plenty of bins, fewer (power of two) for small N so that the
     // batches still spread over all SMs instead of serialising 32 bins on a few warps
     const int bpw_log2 = p.bpw_log2;
-#if BPP_TWO_TIER
-    const long long n_full = p.n_full, full_bins = n_full << bpw_log2;
-    const long long n_batches = n_full + (((long long)p.N - full_bins + (1 << p.tail_log2) - 1) >> p.tail_log2);
-#else
     const long long n_batches = ((long long)p.N + (1 << bpw_log2) - 1) >> bpw_log2;
-#endif
     const int n_steps = FAST ? max(io.n_steps, 1) : 1;
     // Several env steps per launch on an env small enough that every warp owns at most one batch: its tiles stay in shared
     // memory from the first step to the last (one bulk load, one bulk store per launch instead of per step).
@@ -172,14 +167,8 @@ __global__ void __launch_bounds__(kThreads, TMA ? tma_min_blocks(ROT, TMA) : BPP
     for (int step = 0; step < n_steps; ++step) {
     for (long long batch = (long long)blockIdx.x * kWarpsPerBlock + warp; batch < n_batches;
          batch += (long long)gridDim.x * kWarpsPerBlock) {
-#if BPP_TWO_TIER
-        const int blog = batch < n_full ? bpw_log2 : p.tail_log2;
-        const long long bin0 = batch < n_full ? batch << bpw_log2 : full_bins + ((batch - n_full) << p.tail_log2);
-        const int nb = (int)min((long long)(1 << blog), (long long)p.N - bin0);
-#else
         const long long bin0 = batch << bpw_log2;
         const int nb = (int)min((long long)(1 << bpw_log2), (long long)p.N - bin0);
-#endif
         const bool have = lane < nb;
         const long long mybin = have ? bin0 + lane : bin0;
         const unsigned long long gid = p.global_offset + (unsigned long long)mybin;
@@ -237,11 +226,7 @@ __global__ void __launch_bounds__(kThreads, TMA ? tma_min_blocks(ROT, TMA) : BPP
                         const int z = (s.box >> 16) & 0xff;
                         const int c00 = w[0], c10 = w[(x - 1) * W], c01 = w[y - 1], c11 = w[(x - 1) * W + y - 1];
                         int m, cnt;
-#if BPP_LANE_CHECK_WORDS
-                        if (y <= 5) window_stats_rows5_words(w, W, x, y, m, cnt);
-#else
                         if (y <= 5) window_stats_rows5<uint8_t>(w, W, x, y, m, cnt);
-#endif
                         else window_stats<uint8_t>(w, W, x, y, m, cnt);
                         const bool ok = accept<1>(m, cnt, thr_cur, z, H, c00, c10, c01, c11);
                         act = (act & 0x003fffffu) | (1u << 23) | (ok ? (1u << 22) | ((uint32_t)(m + z) << 24) : 0u);
@@ -462,9 +447,9 @@ __global__ void __launch_bounds__(kThreads, TMA ? tma_min_blocks(ROT, TMA) : BPP
 #pragma unroll 1
                     for (int k = lane; k < q4; k += 32) {
                         store_out(o4 + k, bytes_to_float4(t32[k]));
-                        store_out(o4 + q4 + k, kPlaneLut ? plane_lut[bx] : make_float4(fx, fx, fx, fx));
-                        store_out(o4 + 2 * q4 + k, kPlaneLut ? plane_lut[by] : make_float4(fy, fy, fy, fy));
-                        store_out(o4 + 3 * q4 + k, kPlaneLut ? plane_lut[bz] : make_float4(fz, fz, fz, fz));
+                        store_out(o4 + q4 + k, plane_lut[bx]);
+                        store_out(o4 + 2 * q4 + k, plane_lut[by]);
+                        store_out(o4 + 3 * q4 + k, plane_lut[bz]);
                     }
                 } else {
 #pragma unroll 1
@@ -667,13 +652,7 @@ static cudaError_t launch_t(const EnvParams &p, const StepIO &io, int mode, int 
         if (force && force[0] >= '0' && force[0] <= '5') q.bpw_log2 = force[0] - '0';
         if (TMA && q.bpw_log2 > TMA) q.bpw_log2 = TMA;
     }
-#if BPP_TWO_TIER
-    const BatchPlan plan = choose_batches(p.N, cap * kWarpsPerBlock);
-    q.bpw_log2 = plan.full_log2; q.n_full = plan.n_full; q.tail_log2 = plan.tail_log2;
-    const long long batches = plan.n_full + plan.n_tail;
-#else
     const long long batches = ((long long)p.N + (1 << q.bpw_log2) - 1) >> q.bpw_log2;
-#endif
     const long long want = (batches + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int grid = (int)(want < cap ? want : cap);
     BPP_LAUNCH((bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST, TMA>), grid, kThreads, smem, st, q, io, mode);
@@ -686,7 +665,7 @@ static cudaError_t launch_rv(const EnvParams &p, const StepIO &io, int mode, boo
     const bool fast = mode == kModeStep && io.obs && io.mask && io.done &&
                       ((io.reward && io.counter && io.ratio && io.sample) || io.packed);
     const int cs = (vec4 && p.L == p.W && (p.L == 10 || p.L == 20)) ? p.L : 0;
-    if (cs == 10 && fast && kTmaBuild && !BPP_TWO_TIER) {
+    if (cs == 10 && fast && kTmaBuild) {
         // bulk-copy path.  Big envs without rotation: 32-bin batches (3 CTAs per SM) while they still give 80 % of those
         // warps a batch; otherwise 16-bin batches at 4-5 CTAs per SM (measured: profiles/r2d_ab_trimmed.jsonl).
         constexpr int kBig = tma_bpw_log2(ROT);

@@ -88,8 +88,6 @@ def lib(defines=()):
         l.emul_debug_draws.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]
         l.emul_set_lane_order.restype = None
         l.emul_set_lane_order.argtypes = [C.c_int]
-        l.emul_choose_batches.restype = None
-        l.emul_choose_batches.argtypes = [C.c_longlong, C.c_longlong, C.c_void_p]
         _libs[key] = l
     return _libs[key]
 
@@ -270,13 +268,6 @@ def check_box(plain, query, size, variant=1, defines=()):
     out = np.full(plain.shape[0], -7, dtype=np.int32)
     assert lib(defines).emul_check_box(_ptr(plain), _ptr(query), plain.shape[0], L, W, H, variant, _ptr(out)) == 0
     return out
-
-
-def choose_batches(N, warps, defines=()):
-    """bpp_params.h choose_batches(): (full_log2, tail_log2, n_full, n_tail)."""
-    out = np.zeros(4, dtype=np.int64)
-    lib(defines).emul_choose_batches(int(N), int(warps), _ptr(out))
-    return tuple(int(v) for v in out)
 
 
 def set_lane_order(order, defines=()):

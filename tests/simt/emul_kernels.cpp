@@ -131,11 +131,4 @@ int emul_debug_draws(unsigned long long seed, uint32_t domain, uint32_t aux, uns
 unsigned long long emul_collectives(void) { return simt::M.collectives; }
 void emul_set_lane_order(int order) { simt::g_lane_order = order; }
 
-// choose_batches() of bpp_params.h (the BPP_TWO_TIER launch rule): out = {full_log2, tail_log2, n_full, n_tail}
-void emul_choose_batches(long long N, long long warps, long long *out)
-{
-    const BatchPlan b = choose_batches(N, warps);
-    out[0] = b.full_log2; out[1] = b.tail_log2; out[2] = b.n_full; out[3] = b.n_tail;
-}
-
 }  // extern "C"

@@ -22,13 +22,7 @@ import emul   # noqa: E402
 # 16-bit-pair mask sweep, lane-per-bin placement check, single sweep for square items under rotation) and the one with
 # every switch off, which tools/ab_bench.py keeps as the timing baseline
 BASELINE = ("BPP_PACKED_SWEEP=0", "BPP_LANE_CHECK=0", "BPP_SQUARE_COPY=0", "BPP_PLAIN_STORES=0")
-# candidates not yet timed on a B200 (build variant "lsu"): even / odd pair words in separate halves, observation planes
-# converted in registers, word loads in the lane-per-bin check
-SPLIT = ("BPP_PAIRS_SPLIT=1", "BPP_PLANE_LUT=0", "BPP_LANE_CHECK_WORDS=1")
 VARIANTS = [pytest.param((), id="default"), pytest.param(BASELINE, id="baseline")]
-# the candidates are not shipped: their tests (two more g++ builds of the kernels, ~2 min) run with BPP_TEST_CANDIDATES=1
-candidates = pytest.mark.skipif(os.environ.get("BPP_TEST_CANDIDATES", "") != "1",
-                                reason="kernel candidates for the next A/B session: set BPP_TEST_CANDIDATES=1")
 
 
 def run_against_oracle(N, size, rot, variant, gen_kw, T, seed, offset=0, global_n=None, edge_every=0, num_sms=2,
@@ -64,7 +58,7 @@ def run_against_oracle(N, size, rot, variant, gen_kw, T, seed, offset=0, global_
     return e.metrics_dict()
 
 
-@pytest.mark.parametrize("defines", VARIANTS + [pytest.param(SPLIT, id="lsu-candidates", marks=candidates)])
+@pytest.mark.parametrize("defines", VARIANTS)
 @pytest.mark.parametrize("rot,variant", [(False, 2), (True, 2), (True, 1)])
 def test_step_kernel_rs_10cube(rot, variant, defines):
     # the compile-time 10x10 fast path (CS = 10, FAST), 32-bin warp batches with a ragged tail, several batches per warp
@@ -73,7 +67,7 @@ def test_step_kernel_rs_10cube(rot, variant, defines):
     assert m["episodes"] > 300
 
 
-@pytest.mark.parametrize("defines", VARIANTS + [pytest.param(SPLIT, id="lsu-candidates", marks=candidates)])
+@pytest.mark.parametrize("defines", VARIANTS)
 def test_step_kernel_20cube_and_small_batches(defines):
     # CS = 20; few bins on "many SMs" -> the batch-size rule picks fewer bins per warp
     run_against_oracle(40, (20, 20, 20), False, 2, dict(gen="rs"), T=40, seed=99, num_sms=8, blocks_per_sm=2, defines=defines)
@@ -191,30 +185,6 @@ def test_random_small_configurations(seed):
     N = int(rng.integers(1, 90))
     run_against_oracle(N, (L, W, H), rot, variant, dict(gen="rs", item_set=items), T=12, seed=seed, edge_every=5,
                        num_sms=int(rng.integers(1, 4)), blocks_per_sm=int(rng.integers(1, 3)))
-
-
-TWO_TIER = ("BPP_TWO_TIER=1",)         # candidate not yet timed on a B200 (build variant "tier")
-
-
-def test_two_tier_batch_plan():
-    """choose_batches(): whole rounds of large batches, then one round of small ones; every bin exactly once."""
-    assert emul.choose_batches(1 << 19, 4736) == (5, 4, 3 * 4736, 4352)       # target: 3 rounds of 32 + one of 16 (was 4 of 32)
-    assert emul.choose_batches(262144, 4736) == (4, 3, 3 * 4736, 4352)        # configs[3]: 3 x 16 + 8 (was 2 x 32)
-    assert emul.choose_batches(65536, 4736)[1:] == (4, 0, 4096)               # configs[2]: one round of 16, as before
-    rng = np.random.default_rng(5)
-    for _ in range(300):
-        N, warps = int(rng.integers(1, 3_000_000)), int(rng.integers(1, 6000))
-        fl, tl, n_full, n_tail = emul.choose_batches(N, warps)
-        assert 0 <= tl <= fl <= 5 and n_full % warps == 0 and n_tail <= warps
-        rest = N - (n_full << fl)
-        assert 0 <= rest <= n_tail << tl and (n_tail == 0 or rest > (n_tail - 1) << tl)
-
-
-@candidates
-@pytest.mark.parametrize("n,num_sms,bps", [(300, 2, 1), (777, 1, 2), (40, 8, 2), (1000, 3, 1)])
-def test_two_tier_batches_through_the_kernel(n, num_sms, bps):
-    run_against_oracle(n, (10, 10, 10), True, 2, dict(gen="rs"), T=10, seed=n, edge_every=4, num_sms=num_sms, blocks_per_sm=bps,
-                       defines=TWO_TIER)
 
 
 def test_extreme_sizes():

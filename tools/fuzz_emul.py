@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised campaign: the interpreted kernels (tests/simt) against the oracle over random configurations.
 
-    python tools/fuzz_emul.py [--minutes 10] [--seed 0] [--defines BPP_PAIRS_SPLIT=1 ...]
+    python tools/fuzz_emul.py [--minutes 10] [--seed 0] [--defines BPP_TMA=0 ...]
 
 Bin sizes 1..32, heights 1..255, item sets with dims 1..(side+2), both mask rules, rotation, rs / replay / cut1 / cut2,
 ragged N, random grid shapes, out-of-range actions, and the three lane schedules of the interpreter.  Stops at the first
