@@ -456,7 +456,9 @@ def main():
                 if name == "cfg1":
                     # small envs are launch-bound: K env steps per launch (bpp_step_packed with n_steps = K)
                     extra["multi_step"] = time_multi_step(ra, K=16, launches=40)
-                    extra["note"] = "one launch per step is launch-latency bound at 4096 bins; multi_step runs 16 env steps per launch"
+                    extra["cuda_graph"] = time_graph(ra, K=16, replays=40)
+                    extra["note"] = ("one launch per step is launch-latency bound at 4096 bins; multi_step runs 16 env steps per "
+                                     "launch, cuda_graph replays a captured graph of 16 single-step launches")
                 aux[key] = aux_line(ra, msa, extra)
                 ra.close()
 
@@ -520,6 +522,39 @@ def time_multi_step(r, K, launches):
     ms = e0.elapsed_time(e1) / (launches * K)
     r.bufs, r.k = [e.sample_t, r.bufs[1] if r.bufs[0] is e.sample_t else r.bufs[0]], 0
     return {"env_steps_per_launch": K, "ms_per_env_step": ms, "value": r.N / (ms * 1e-3), "unit": "env-steps/s"}
+
+
+def time_graph(r, K, replays):
+    """env-steps/s with K single-step launches captured into one CUDA graph (in-place action buffer) and replayed."""
+    import torch
+    e, dev = r.env, r.dev
+    a = r.bufs[r.k & 1]
+    if a is not e.sample_t:
+        e.sample_t.copy_(a)
+    torch.cuda.synchronize(dev)
+    s = torch.cuda.Stream(device=dev)
+    g = torch.cuda.CUDAGraph()
+    try:
+        with torch.cuda.stream(s):
+            e.step_device(e.sample_t)
+            torch.cuda.synchronize(dev)
+            with torch.cuda.graph(g, stream=s):
+                for _ in range(K):
+                    e.step_device(e.sample_t)
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s)
+            for _ in range(replays):
+                g.replay()
+            e1.record(s)
+            torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / (replays * K)
+    except Exception as ex:      # noqa: BLE001
+        return {"error": repr(ex)}
+    r.bufs, r.k = [e.sample_t, r.bufs[1] if r.bufs[0] is e.sample_t else r.bufs[0]], 0
+    return {"env_steps_per_graph": K, "ms_per_env_step": ms, "value": r.N / (ms * 1e-3), "unit": "env-steps/s"}
 
 
 def reference_subprocess(args):

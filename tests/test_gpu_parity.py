@@ -617,3 +617,32 @@ def test_int32_strided_actions_from_previous_records(env_mod):
     a.close(); b.close()
     for h in hb:
         h.free()
+
+
+def test_steps_are_cuda_graph_capturable(env_mod):
+    """After one ordinary call (which sizes the launch), bpp_step makes no call that a stream capture forbids: 8 steps
+    captured into one CUDA graph and replayed give what 8 plain calls give (small envs are launch-bound; a graph or
+    bpp_step_packed's n_steps remove the per-step launch cost)."""
+    import torch
+    a = env_mod.BinPackingVecEnv(4096, enable_rotation=True, seed=11, want_sample=True)
+    b = env_mod.BinPackingVecEnv(4096, enable_rotation=True, seed=11, want_sample=True)
+    a.reset(); b.reset()
+    for env in (a, b):
+        env.step_device(env.sample_t)               # in place: the kernel reads a bin's action before it writes its next one
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(8):
+                a.step_device(a.sample_t)
+    for rnd in range(3):
+        g.replay()
+        for _ in range(8):
+            b.step_device(b.sample_t)
+        torch.cuda.synchronize()
+        assert torch.equal(a.obs, b.obs) and torch.equal(a.location_masks, b.location_masks) and torch.equal(a.sample_t, b.sample_t)
+        assert torch.equal(a.reward_t, b.reward_t) and torch.equal(a.done_t, b.done_t)
+    ma, mb = a.metrics(), b.metrics()
+    assert (ma["episodes"], ma["sum_counter"], ma["sum_vol"]) == (mb["episodes"], mb["sum_counter"], mb["sum_vol"])
+    a.close(); b.close()
