@@ -76,6 +76,15 @@ __device__ __forceinline__ void store_out(T *p, T v)
 #define BPP_TMA 1
 #endif
 constexpr bool kTmaBuild = BPP_TMA != 0;
+// Bulk-copy path for 20x20 bins: log2 of the bins per warp batch (0 = off: the ordinary path).  A 20x20 bin needs 1.6 KB
+// per float32 plane, so shared memory only holds small batches and the table of constant planes covers the values 0..7
+// (larger item sides take ordinary stores).  Measured at 262 144 bins (profiles/r2j_ab_tma20.jsonl): 8-bin batches at
+// 2 CTAs per SM 0.414-0.424 ms against 0.476-0.482 ms on the ordinary path; 4-bin x 3 CTAs 0.453, 16-bin x 1 CTA 0.560.
+#ifndef BPP_TMA20
+#define BPP_TMA20 3
+#endif
+// constant observation planes kept per CTA on the bulk-copy path: values 0 .. tma_lut_planes(cs) - 1
+__host__ __device__ constexpr int tma_lut_planes(int cs) { return cs <= 10 ? cs + 1 : 8; }
 // bins per warp batch of that path (log2): bounded by shared memory -- a batch's tiles and staged records live there.
 // Measured on a B200 (profiles/r2c_ab_tma_variants.jsonl): without rotation 32-bin batches at 3 CTAs per SM beat 16-bin
 // batches at 5 (the lane-per-bin phases are amortised over twice the bins, 0.239 vs 0.246 ms); with rotation -- twice

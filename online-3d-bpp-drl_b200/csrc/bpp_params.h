@@ -56,7 +56,7 @@ inline size_t step_smem_bytes(const EnvParams &p, int tma = 0, int rot = 0)     
     if (tma) {
         const int bins = 1 << tma, A = cs * cs, M = A * (rot ? 2 : 1);
         const size_t per_warp = (size_t)bins * ((A + 15) & ~15) + ((M + 15) & ~15) + pair_bytes(cs) + 4 * (size_t)(A + M) + (size_t)bins * 80;
-        return (size_t)(cs + 1) * 4 * A + (size_t)kWarpsPerBlock * per_warp;
+        return (size_t)tma_lut_planes(cs) * 4 * A + (size_t)kWarpsPerBlock * per_warp;
     }
     return (size_t)kWarpsPerBlock * (size_t)(p.A_pad + p.M_pad + pair_bytes(cs)) + (size_t)kWarpsPerBlock * 32 * 80;
 }

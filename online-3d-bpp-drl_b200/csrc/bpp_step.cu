@@ -27,7 +27,10 @@ constexpr bool kUniformOps = BPP_UNIFORM != 0;
 // Resident CTAs per SM the register allocator must allow for the bulk-copy instantiations.  Their shared memory holds a
 // whole batch of tiles and records, so the batch size decides: 32-bin batches fit 3 CTAs per SM, 16-bin batches 5 (4 with
 // rotation).  Both are built; the launch picks per env size (launch_rv below).
-__host__ __device__ constexpr int tma_min_blocks(int rot, int bpw_log2) { return bpw_log2 >= 5 ? 3 : (rot ? 4 : 5); }
+__host__ __device__ constexpr int tma_min_blocks(int rot, int bpw_log2, int cs = 10)
+{
+    return cs > 10 ? (bpw_log2 >= 4 ? 1 : (bpw_log2 >= 3 || rot ? 2 : 3)) : (bpw_log2 >= 5 ? 3 : (rot ? 4 : 5));
+}
 
 namespace bpp {
 
@@ -89,7 +92,7 @@ __device__ __forceinline__ uint32_t episode_item(const EnvParams &p, long long b
 // CS = compile-time bin side (L == W == CS; 10 and 20 are the reference's configurations, 0 = any size read
 // from EnvParams), FAST = the rollout case (mode == step and every output requested) with the checks folded.
 template <int ROT, int VARIANT, bool VEC4, int CS, bool FAST, int TMA>
-__global__ void __launch_bounds__(kThreads, TMA ? tma_min_blocks(ROT, TMA) : BPP_MIN_BLOCKS) bpp_step_kernel(const EnvParams p, const StepIO io, const int mode_arg)
+__global__ void __launch_bounds__(kThreads, TMA ? tma_min_blocks(ROT, TMA, CS) : BPP_MIN_BLOCKS) bpp_step_kernel(const EnvParams p, const StepIO io, const int mode_arg)
 {
     static_assert(!TMA || (FAST && VEC4 && CS > 0), "the bulk-copy path is the rollout path of the compile-time bin sizes");
     const int mode = FAST ? (int)kModeStep : mode_arg;
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, TMA ? tma_min_blocks(ROT, TMA) : BPP
     constexpr int kTmaBins = TMA ? 1 << TMA : 32;        // TMA = log2 of the bins per warp batch (0: ordinary path)
     constexpr int kTmaTiles = TMA ? kTmaBins * ((CS * CS + 15) & ~15) : 0;
     constexpr int kTmaStage = TMA ? 4 * CS * CS * (ROT ? 3 : 2) : 0;
-    constexpr int kTmaLutN = CS + 1;                  // constant planes for the values 0 .. CS (item sides up to the bin side)
+    constexpr int kTmaLutN = tma_lut_planes(CS);      // constant planes for the values 0 .. kTmaLutN - 1
     constexpr int kTmaLutBytes = TMA ? kTmaLutN * 4 * CS * CS : 0;
     const int warp_bytes = TMA ? kTmaTiles + M_pad + pair_bytes(CS) + kTmaStage + kTmaBins * (16 * kRecQuads)
                                : A_pad + M_pad + pair_bytes(CS);
@@ -680,6 +683,7 @@ static cudaError_t launch_rv(const EnvParams &p, const StepIO &io, int mode, boo
     }
     if (cs == 10) return fast ? launch_t<ROT, VARIANT, true, 10, true, 0>(p, io, mode, num_sms, st)
                               : launch_t<ROT, VARIANT, true, 10, false, 0>(p, io, mode, num_sms, st);
+    if (cs == 20 && fast && kTmaBuild && BPP_TMA20 > 0) return launch_t<ROT, VARIANT, true, 20, true, BPP_TMA20>(p, io, mode, num_sms, st);
     if (cs == 20) return fast ? launch_t<ROT, VARIANT, true, 20, true, 0>(p, io, mode, num_sms, st)
                               : launch_t<ROT, VARIANT, true, 20, false, 0>(p, io, mode, num_sms, st);
     return vec4 ? launch_t<ROT, VARIANT, true, 0, false, 0>(p, io, mode, num_sms, st)
