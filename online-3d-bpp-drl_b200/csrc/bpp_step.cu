@@ -625,6 +625,10 @@ static cudaError_t launch_t(const EnvParams &p, const StepIO &io, int mode, int 
         }
         resident = blocks_per_sm[dev];
     }
+    {   // experiment hook: BPP_MAX_CTAS=k caps the resident CTAs per SM the grid is sized for
+        static const char *force = std::getenv("BPP_MAX_CTAS");
+        if (force && force[0] >= '1' && force[0] <= '9' && resident > force[0] - '0') resident = force[0] - '0';
+    }
     const long long cap = (long long)num_sms * resident;
     // largest power-of-two batch (<= 32 bins per warp; <= 2^TMA on the bulk-copy path, whose shared memory
     // holds a batch's tiles) that still gives at least 80 % of the resident warps a batch
