@@ -79,46 +79,53 @@ __device__ __forceinline__ void warp_erase(T *a, int idx, int n, int lane)
 __device__ int order_cut1_registers(const EnvParams &p, GenRng &g, uint32_t *out, const Piece *leaf, int n_leaf, int cap, int lane)
 {
     const unsigned lt = (1u << lane) - 1u;
-    Piece q[2];
+    // per slot: the piece's item word (x | y << 8 | z << 16), its footprint bounds, the z of its bottom and top face
+    uint32_t item[2];
+    int x0[2], x1[2], y0[2], y1[2], zb[2], zt[2];
     int rem[2], pos[2];                                  // uncovered bottom area (waiting pieces), candidate-list position
     unsigned c[2];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         const int i = s * 32 + lane;
-        q[s] = i < n_leaf ? leaf[i] : 0;
         const bool valid = i < n_leaf;
-        rem[s] = (valid && plz(q[s]) > 0) ? px(q[s]) * py(q[s]) : 0;
-        c[s] = __ballot_sync(kFull, valid && plz(q[s]) == 0);          // first scan: shadow == 0, ready <=> lz == 0
+        const Piece q = valid ? leaf[i] : 0;
+        item[s] = (uint32_t)q & 0x00ffffffu;
+        x0[s] = plx(q); x1[s] = x0[s] + px(q); y0[s] = ply(q); y1[s] = y0[s] + py(q); zb[s] = plz(q); zt[s] = zb[s] + pz(q);
+        rem[s] = (valid && zb[s] > 0) ? px(q) * py(q) : 0;
+        c[s] = __ballot_sync(kFull, valid && zb[s] == 0);               // first scan: shadow == 0, ready <=> lz == 0
     }
     pos[0] = (c[0] >> lane) & 1u ? __popc(c[0] & lt) : -1;
     pos[1] = (c[1] >> lane) & 1u ? __popc(c[0]) + __popc(c[1] & lt) : -1;
     int n_cand = __popc(c[0]) + __popc(c[1]), n_out = 0;
     while (n_cand > 0) {                                                  // :113-115: no candidate -> sentinel from now on
         const int idx = (int)__umulhi(g.next(), (uint32_t)n_cand);        // random.randint(0, len(candidates) - 1), :116
-        const unsigned s0 = __ballot_sync(kFull, pos[0] == idx), s1 = __ballot_sync(kFull, pos[1] == idx);
-        const int src = __ffs(s0 | s1) - 1;
-        const Piece e = __shfl_sync(kFull, pos[0] == idx ? q[0] : q[1], src);      // candidates.pop(idx)
+        const bool mine0 = pos[0] == idx, mine1 = pos[1] == idx;
+        const int src = __ffs(__ballot_sync(kFull, mine0 || mine1)) - 1;
+        // candidates.pop(idx): the chosen piece's item word, footprint (4 x 8 bits) and top face reach every lane
+        const uint32_t e_item = __shfl_sync(kFull, mine0 ? item[0] : item[1], src);
+        const uint32_t e_box = __shfl_sync(kFull, mine0 ? (uint32_t)(x0[0] | (x1[0] << 8) | (y0[0] << 16) | (y1[0] << 24))
+                                                        : (uint32_t)(x0[1] | (x1[1] << 8) | (y0[1] << 16) | (y1[1] << 24)), src);
+        const int top = __shfl_sync(kFull, mine0 ? zt[0] : zt[1], src);
 #pragma unroll
         for (int s = 0; s < 2; ++s) pos[s] = pos[s] == idx ? -1 : (pos[s] > idx ? pos[s] - 1 : pos[s]);
         --n_cand;
-        int ox = px(e), oy = py(e);
+        uint32_t emit = e_item;
         if (p.rot) {                                                      // :120-126
             const uint32_t coin = g.next();
-            if (coin >= 0x80000000u) { ox = py(e); oy = px(e); }
+            if (coin >= 0x80000000u) emit = (e_item & 0x00ff0000u) | ((e_item & 0xffu) << 8) | ((e_item >> 8) & 0xffu);
         }
         if (n_out < cap) {
-            if (lane == 0) out[n_out] = pack_item(ox, oy, pz(e));
+            if (lane == 0) out[n_out] = emit;
             ++n_out;
         }
         // _update + _add_candidate, :109-110, :98-107
-        const int top = plz(e) + pz(e), ex0 = plx(e), ex1 = ex0 + px(e), ey0 = ply(e), ey1 = ey0 + py(e);
+        const int ex0 = e_box & 0xff, ex1 = (e_box >> 8) & 0xff, ey0 = (e_box >> 16) & 0xff, ey1 = e_box >> 24;
         bool fresh[2];
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             fresh[s] = false;
-            if (rem[s] > 0 && plz(q[s]) == top) {
-                const int wx = min(ex1, plx(q[s]) + px(q[s])) - max(ex0, plx(q[s]));
-                const int wy = min(ey1, ply(q[s]) + py(q[s])) - max(ey0, ply(q[s]));
+            if (rem[s] > 0 && zb[s] == top) {
+                const int wx = min(ex1, x1[s]) - max(ex0, x0[s]), wy = min(ey1, y1[s]) - max(ey0, y0[s]);
                 if (wx > 0 && wy > 0) {
                     rem[s] -= wx * wy;
                     fresh[s] = rem[s] == 0;
@@ -286,14 +293,17 @@ __device__ int gen_cut1(const EnvParams &p, GenRng &g, uint32_t *out, Piece *lea
 //     "the iterator skips the element that slid into the vacated slot" is i += 2 -- and the list is compacted between
 //     sweeps with one ballot per 32 entries;
 //   * the stable sort by low_bound (:137-138): one ballot per level and 32 entries.
-// `inv`: cap + 64 pieces; `val`: cap words x | y << 8 | z << 16 | lz << 24; `draws`: 128 words.
-__device__ int gen_cut2(const EnvParams &p, GenRng &g, uint32_t *out, Piece *inv, uint32_t *val, uint32_t *draws, int cap, int lane)
+// A piece is two words here: sizes x | y << 8 | z << 16 and position lx | ly << 8 | lz << 16 (a cut along axis a then
+// is an add / subtract at bit 8a, and a field is one extract).  `inv`: cap + 64 pieces (size word 0 = tombstone);
+// `val`: cap words x | y << 8 | z << 16 | lz << 24; `draws`: 128 words.
+__device__ int gen_cut2(const EnvParams &p, GenRng &g, uint32_t *out, Piece *inv_, uint32_t *val, uint32_t *draws, int cap, int lane)
 {
+    uint2 *inv = reinterpret_cast<uint2 *>(inv_);
     const int lo = p.lo[0], hi = p.hi[0];
     const unsigned lt = (1u << lane) - 1u;
     int n_inv = 1, n_val = 0;
     uint32_t k = 0;                                                       // draws consumed (even)
-    if (lane == 0) inv[0] = mk_piece(p.L, p.W, p.H, 0, 0, 0);
+    if (lane == 0) inv[0] = make_uint2((uint32_t)p.L | ((uint32_t)p.W << 8) | ((uint32_t)p.H << 16), 0u);
     while (n_inv > 0) {                                                   // gen_benchmark, mdCreator.py:117-135
         int i = 0, n_phys = n_inv;
         while (i < n_phys) {
@@ -305,13 +315,14 @@ __device__ int gen_cut2(const EnvParams &p, GenRng &g, uint32_t *out, Piece *inv
                 reinterpret_cast<uint4 *>(draws)[lane] = blk;
                 __syncwarp();
             }
-            Piece b = 0;
+            uint2 b = make_uint2(0u, 0u);
             if (lane == 0) b = inv[i];
-            b = __shfl_sync(kFull, b, 0);
-            const unsigned fl = (unsigned)(px(b) > hi) | ((unsigned)(py(b) > hi) << 1) | ((unsigned)(pz(b) > hi) << 2);   // benchmark_split, :60-66
+            const uint32_t d = __shfl_sync(kFull, b.x, 0), o = __shfl_sync(kFull, b.y, 0);
+            const int x = d & 0xff, y = (d >> 8) & 0xff, z = (d >> 16) & 0xff;
+            const unsigned fl = (unsigned)(x > hi) | ((unsigned)(y > hi) << 1) | ((unsigned)(z > hi) << 2);   // benchmark_split, :60-66
             if (fl == 0u) {                                               // unreachable for validated ranges (no draw is taken)
-                if (lane == 0) inv[i] = 0;
-                if (n_val < cap) { if (lane == 0) val[n_val] = pack_item(px(b), py(b), pz(b)) | ((uint32_t)plz(b) << 24); ++n_val; }
+                if (lane == 0) inv[i].x = 0u;
+                if (n_val < cap) { if (lane == 0) val[n_val] = d | ((o >> 16) << 24); ++n_val; }
                 i += 2;
                 continue;
             }
@@ -319,32 +330,33 @@ __device__ int gen_cut2(const EnvParams &p, GenRng &g, uint32_t *out, Piece *inv
             k += 2u;
             const int r = (int)__umulhi(u0, (uint32_t)__popc(fl));        // random.choice(flags), :68: the r-th oversize axis
             const unsigned rest = r == 0 ? fl : (r == 1 ? (fl & (fl - 1u)) : 4u);
-            const int ax = __ffs(rest) - 1;
-            const int side = ax == 0 ? px(b) : (ax == 1 ? py(b) : pz(b));
+            const int ax = __ffs(rest) - 1, sh = 8 * ax;
+            const int side = (int)((d >> sh) & 0xffu);
             const int cut = 1 + (int)__umulhi(u1, (uint32_t)side);        // randint(1, side)
             if (cut < lo || side - cut < lo) { ++i; continue; }            // rejected, retried in the next sweep
-            Piece sub[2];
-            if (ax == 0) { sub[0] = mk_piece(cut, py(b), pz(b), plx(b), ply(b), plz(b)); sub[1] = mk_piece(px(b) - cut, py(b), pz(b), plx(b) + cut, ply(b), plz(b)); }        // :70-79
-            else if (ax == 1) { sub[0] = mk_piece(px(b), cut, pz(b), plx(b), ply(b), plz(b)); sub[1] = mk_piece(px(b), py(b) - cut, pz(b), plx(b), ply(b) + cut, plz(b)); }   // :80-89
-            else { sub[0] = mk_piece(px(b), py(b), pz(b) - cut, plx(b), ply(b), plz(b)); sub[1] = mk_piece(px(b), py(b), cut, plx(b), ply(b), plz(b) + pz(b) - cut); }        // :90-99
-            if (lane == 0) inv[i] = 0;                                    // invalid_box.remove(box): tombstone
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {                                 // is_valid, :110-115
-                const Piece q = sub[s];
-                const bool ok = px(q) >= lo && px(q) <= hi && py(q) >= lo && py(q) <= hi && pz(q) >= lo && pz(q) <= hi;
-                if (ok) { if (n_val < cap) { if (lane == 0) val[n_val] = pack_item(px(q), py(q), pz(q)) | ((uint32_t)plz(q) << 24); ++n_val; } }
-                else if (n_phys < cap + 64) { if (lane == 0) inv[n_phys] = q; ++n_phys; }
-            }
+            // :70-99: along x / y the first part has size `cut` and the second starts `cut` further; along z the first part
+            // keeps the bottom with size z - cut and the second (size cut) sits on top of it
+            const int a = ax == 2 ? side - cut : cut;
+            const uint32_t d1 = d - ((uint32_t)(side - a) << sh), d2 = d - ((uint32_t)a << sh), o2 = o + ((uint32_t)a << sh);
+            if (lane == 0) inv[i].x = 0u;                                 // invalid_box.remove(box): tombstone
+            // is_valid, :110-115: all three sizes within [lo, hi]; both new sizes are >= lo by the test above
+            const unsigned in_range = (unsigned)(x >= lo && x <= hi) | ((unsigned)(y >= lo && y <= hi) << 1) | ((unsigned)(z >= lo && z <= hi) << 2);
+            const bool others = (in_range | (1u << ax)) == 7u;
+            const bool ok1 = others && a <= hi, ok2 = others && side - a <= hi;
+            if (ok1) { if (n_val < cap) { if (lane == 0) val[n_val] = d1 | ((o >> 16) << 24); ++n_val; } }
+            else if (n_phys < cap + 64) { if (lane == 0) inv[n_phys] = make_uint2(d1, o); ++n_phys; }
+            if (ok2) { if (n_val < cap) { if (lane == 0) val[n_val] = d2 | ((o2 >> 16) << 24); ++n_val; } }
+            else if (n_phys < cap + 64) { if (lane == 0) inv[n_phys] = make_uint2(d2, o2); ++n_phys; }
             i += 2;                                                       // the iterator skips the element that slid into slot i
         }
         int keep = 0;                                                     // drop the tombstones, 32 entries per ballot
         __syncwarp();
         for (int j0 = 0; j0 < n_phys; j0 += 32) {
             const int j = j0 + lane;
-            const Piece q = j < n_phys ? inv[j] : 0;
-            const unsigned live = __ballot_sync(kFull, q != 0);
+            const uint2 q = j < n_phys ? inv[j] : make_uint2(0u, 0u);
+            const unsigned live = __ballot_sync(kFull, q.x != 0u);
             __syncwarp();                                                 // every lane has read its entry of this chunk
-            if (q != 0) inv[keep + __popc(live & lt)] = q;
+            if (q.x != 0u) inv[keep + __popc(live & lt)] = q;
             keep += __popc(live);
         }
         __syncwarp();
