@@ -16,5 +16,9 @@ for w in target target_rot cfg2 cfg3; do
   timeout 150 ncu --set full --clock-control none --import-source on -k regex:bpp_step_kernel --launch-skip 14 --launch-count 1 -f -o gpurun_out/prof_${T}_$w \
       python bench.py --workload $w --steps 5 --warmup 10 --no-cpu-baseline --no-aux --e2e-steps 3 > gpurun_out/ncu_${T}_$w.log 2>&1; echo "ncu $w exit $?"
 done
+for w in cut1 cut2; do
+  timeout 120 ncu --set full --clock-control none --import-source on -k regex:bpp_gen --launch-skip 12 --launch-count 1 -f -o gpurun_out/prof_${T}_gen_$w \
+      python bench.py --workload $w --steps 5 --warmup 10 --no-cpu-baseline --no-aux --e2e-steps 3 > gpurun_out/ncu_${T}_gen_$w.log 2>&1; echo "ncu gen $w exit $?"
+done
 timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$T.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 3 > gpurun_out/launches_$T.log 2>&1; echo "launch list exit $?"
