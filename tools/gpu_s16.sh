@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}" || exit 1
 mkdir -p gpurun_out
-for c in 9 3 2 1; do
+for c in 9 4 3; do
 BPP_MAX_CTAS=$c python - <<'PY'
 import json, sys, os
 sys.path.insert(0, '.'); sys.path.insert(0, 'online-3d-bpp-drl_b200')
