@@ -646,3 +646,30 @@ def test_steps_are_cuda_graph_capturable(env_mod):
     ma, mb = a.metrics(), b.metrics()
     assert (ma["episodes"], ma["sum_counter"], ma["sum_vol"]) == (mb["episodes"], mb["sum_counter"], mb["sum_vol"])
     a.close(); b.close()
+
+
+def test_packed_host_step_with_ordinary_memory(env_mod):
+    """bpp_step_packed_host with pageable host buffers (numpy arrays): staged through device copies, same records as the
+    zero-copy route; the int32 entry point refuses ordinary memory loudly."""
+    import torch
+    from b200bpp import _cabi, BppError
+    n = 5000
+    a = env_mod.BinPackingVecEnv(n, seed=17, want_sample=True)
+    b = env_mod.BinPackingVecEnv(n, seed=17, want_sample=True)
+    a.reset(); b.reset()
+    lib = _cabi.lib()
+    P = lambda t: C.c_void_p(t.data_ptr())
+    Np = lambda x: x.ctypes.data_as(C.c_void_p)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for t in range(6):
+        act = t2n(a.sample_t).copy()
+        rec, done = np.zeros((n, 4), np.int32), np.zeros(n, np.uint8)
+        _cabi.check(lib.bpp_step_packed_host(b._h, Np(act), P(b.obs), P(b.location_masks), Np(rec), Np(done), P(b.sample_t), st))
+        _, reward, d, infos = a.step(torch.as_tensor(act, device="cuda").view(-1, 1))
+        assert np.array_equal(rec[:, 0].copy().view(np.float32), reward.numpy().reshape(-1)) and np.array_equal(done, d.astype(np.uint8))
+        assert np.array_equal(rec[:, 3].astype(np.int64), t2n(a.sample_t)) and torch.equal(a.obs, b.obs)
+        assert all(infos[i]["counter"] == int(rec[i, 2]) for i in range(0, n, 997))
+    with pytest.raises(BppError):
+        act32 = np.zeros(n, np.int32)
+        _cabi.check(lib.bpp_step_packed_host_i32(b._h, Np(act32), 1, P(b.obs), P(b.location_masks), Np(rec), Np(done), None, st))
+    a.close(); b.close()
