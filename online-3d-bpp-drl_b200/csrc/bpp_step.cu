@@ -1,13 +1,15 @@
 // bpp_step.cu -- the fused per-step kernel of the batched 3D bin-packing environment (sm_100a).
 //
-// One launch per env step.  Persistent CTAs of 8 warps; every warp takes batches of 32 bins through three phases
-// (details at the kernel): scalar work with one LANE per bin, heightmap-tile work with the whole WARP per bin
-// (128-bit staged u8 tile in shared memory, footprint update, mask sweep with two candidate positions per lane in
-// 16-bit register halves and the footprint unrolled at compile time, 128-bit stores of the float32 observation and
-// mask), and the per-bin results again with one lane per bin.
-// HBM-bound integer work by design (no tensor cores); in practice the L1 / shared-memory path is the busiest unit (72 %;
-// issue slots 66 %, DRAM 56 %), see DESIGN.md section 3 and profiles/README.md.  Reference behaviour is cited inline
-// (paths relative to the reference root).
+// One launch per env step (or several steps per launch: StepIO::n_steps).  Persistent CTAs of 8 warps; every warp takes
+// batches of bins through three phases (details at the kernel): scalar work with one LANE per bin, heightmap-tile work
+// with the whole WARP per bin (footprint update, mask sweep with two candidate positions per lane in 16-bit register
+// halves and the footprint unrolled at compile time, float32 observation and mask rows), and the per-bin results again
+// with one lane per bin.  On the rollout instantiations for 10x10 and 20x20 bins the copy engine moves the data: one
+// bulk load / store per batch of tiles (cp.async.bulk + mbarrier), bulk stores of the staged rows and of constant planes.
+// HBM-bound integer work by design (no tensor cores).  At the target workload (2^19 bins of 10x10): 0.229 ms per launch,
+// 0.99 of the measured copy bandwidth by algorithmic bytes, 0.78 by the bytes really moved; issue slots 67 % busy, 24
+// warps per SM -- see DESIGN.md section 3 and profiles/README.md.  Reference behaviour is cited inline (paths relative
+// to the reference root).
 #include <cstdlib>
 #include <mutex>
 
@@ -25,8 +27,8 @@ constexpr bool kUniformOps = BPP_UNIFORM != 0;
 #define BPP_MIN_BLOCKS 4   // resident CTAs per SM the register allocator must allow (8 warps each)
 #endif
 // Resident CTAs per SM the register allocator must allow for the bulk-copy instantiations.  Their shared memory holds a
-// whole batch of tiles and records, so the batch size decides: 32-bin batches fit 3 CTAs per SM, 16-bin batches 5 (4 with
-// rotation).  Both are built; the launch picks per env size (launch_rv below).
+// whole batch of tiles and records, so the batch size decides: at 10x10, 32-bin batches fit 3 CTAs per SM, 16-bin batches 5
+// (4 with rotation) -- both are built and the launch picks per env size (launch_rv below); at 20x20, 8-bin batches fit 2.
 __host__ __device__ constexpr int tma_min_blocks(int rot, int bpw_log2, int cs = 10)
 {
     return cs > 10 ? (bpw_log2 >= 4 ? 1 : (bpw_log2 >= 3 || rot ? 2 : 3)) : (bpw_log2 >= 5 ? 3 : (rot ? 4 : 5));
