@@ -476,7 +476,7 @@ int32_t bpp_step_packed_host(bpp_env *env, const int64_t *actions_host, float *o
         io.done = static_cast<uint8_t *>(env->zc_dev[3]);
     } else {        // ordinary host memory: staged through device buffers
         if (!env->d_results) BPP_CUDA(cudaMalloc(&env->d_results, N * sizeof(bpp_result)));
-        BPP_CUDA(cudaMemcpyAsync(env->d_actions, actions_host, N * sizeof(long long), cudaMemcpyHostToDevice, st));
+        BPP_CUDA(cudaMemcpyAsync(env->d_actions, actions_host, N * sizeof(long long), cudaMemcpyDefault, st));   // host or device actions
         io.actions = env->d_actions;
         io.packed = reinterpret_cast<uint4 *>(env->d_results);
         io.done = env->d_done;
