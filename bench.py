@@ -475,7 +475,8 @@ def main():
                     "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": 17 * N, "ms_per_step": e2e_ms,
                     "api": "bpp_step_packed_host_i32 (bpp_step_packed_host, the call under BinPackingVecEnv.step, with int32 "
                            "actions): actions read from pinned, NUMA-local host memory (the next_action column of the previous "
-                           "step's records), one 16-byte result record (reward, placed volume, counter, next action) + one done "
+                           "step's records: 4 bytes per bin are consumed, the strided read touches the whole 16-byte "
+                           "records), one 16-byte result record (reward, placed volume, counter, next action) + one done "
                            "byte per bin written to pinned host memory, zero-copy over PCIe inside the kernel, stream "
                            "synchronised every step; obs+mask stay on the device as in acktr/envs.py:191; wall clock, max over ranks"},
             "e2e_py": {"value": total_bins / (e2e_py_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": e2e_py_ms,
