@@ -167,6 +167,7 @@ class BinPackingVecEnv(object):
         self._h_done = [self._hbufs[3 + k].view(np.bool_, (N,)) for k in range(2)]
         self._flip = 0
         self._dev_actions = None
+        self._step_args = None
         self._pending = None
         self._t0 = time.time()
         self.venv = None        # get_vec_normalize(envs) walks .venv and must end at None (acktr/utils.py:96-102)
@@ -241,14 +242,25 @@ class BinPackingVecEnv(object):
         self._pending = None
         k = self._flip
         self._flip ^= 1
-        act = self._p(self._dev_actions) if self._dev_actions is not None else C.c_void_p(self._hbufs[0].ptr)
-        with torch.cuda.device(self.device):
-            _cabi.check(self._lib.bpp_step_packed_host(
-                self._h, act, self._p(self.obs), self._p(self.location_masks), C.c_void_p(self._hbufs[1 + k].ptr),
-                C.c_void_p(self._hbufs[3 + k].ptr), self._p(self.sample_t), self._stream()))
+        if self._step_args is None:            # the pointers of a step() call never change: build the ctypes values once
+            self._step_args = [(C.c_void_p(self._hbufs[0].ptr), self._p(self.obs), self._p(self.location_masks),
+                                C.c_void_p(self._hbufs[1 + j].ptr), C.c_void_p(self._hbufs[3 + j].ptr), self._p(self.sample_t))
+                               for j in range(2)]
+            self._lwh = float(np.prod(self.bin_size))
+            self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        h_act, obs_p, mask_p, rec_p, done_p, sample_p = self._step_args[k]
+        act = self._p(self._dev_actions) if self._dev_actions is not None else h_act
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if torch.cuda.current_device() == self._dev_index:       # (the library selects the env's device itself)
+            rc = self._lib.bpp_step_packed_host(self._h, act, obs_p, mask_p, rec_p, done_p, sample_p, stream)
+        else:
+            with torch.cuda.device(self.device):
+                rc = self._lib.bpp_step_packed_host(self._h, act, obs_p, mask_p, rec_p, done_p, sample_p, stream)
+        if rc != 0:
+            _cabi.check(rc)
         self._dev_actions = None
         done = self._h_done[k]
-        infos = LazyInfos(done, self._h_rec[k], float(np.prod(self.bin_size)), self._t0, self.act_len) if self.host_infos else ()
+        infos = LazyInfos(done, self._h_rec[k], self._lwh, self._t0, self.act_len) if self.host_infos else ()
         return self.obs, self._h_reward[k], done, infos
 
     def step(self, actions):
