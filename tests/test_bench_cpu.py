@@ -53,3 +53,21 @@ def test_ab_picker_on_the_recorded_sessions():
     assert pick("r1k_ab_first.jsonl") == "packed"        # before the square copy had a single call site
     assert pick("r1k_ab_final.jsonl") == "fullps"        # = today's default build
     assert pick("does_not_exist.jsonl") == "full"
+
+
+def test_vendored_reference_is_unmodified():
+    """oracle/make_ref.py copies the reference's envs/ acktr/ baselines/ packages byte for byte into oracle/_ref (git-ignored);
+    the manifest's SHA-256 of every file must match the copy and, where the reference tree is present, the source."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import make_ref
+    dest = make_ref.build()
+    if dest is None:
+        import pytest
+        pytest.skip("neither /root/reference nor an earlier oracle/_ref")
+    assert make_ref.verify()
+    import json
+    files = json.load(open(os.path.join(dest, "MANIFEST.json")))["files"]
+    assert "acktr/envs.py" in files and "envs/bpp0/bin3D.py" in files and "baselines/common/vec_env/shmem_vec_env.py" in files
+    # nothing of it is tracked by git: reference sources stay out of this repository's history
+    tracked = subprocess.run(["git", "ls-files", "oracle/_ref"], cwd=ROOT, capture_output=True, text=True).stdout.strip()
+    assert tracked == ""
