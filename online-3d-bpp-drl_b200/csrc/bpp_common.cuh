@@ -496,7 +496,7 @@ __device__ __forceinline__ int sweep_loop(const uint8_t *tile, uint8_t *smask, i
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Packed sweep (rule v2, compile-time footprint and bin side): one lane evaluates the two horizontally adjacent
+// Packed sweep (compile-time footprint and bin side): one lane evaluates the two horizontally adjacent
 // candidate positions (i, j) and (i, j + 1), j even, at once, one position per 16-bit half of a register.
 // `pairs[k]` holds the complemented heights (255 - tile[k]) | (255 - tile[k + 1]) << 16 of cell k and its right
 // neighbour, so the X*Y loads of a lane deliver the windows of both positions.  With g = 255 - h:
@@ -508,6 +508,11 @@ __device__ __forceinline__ int sweep_loop(const uint8_t *tile, uint8_t *smask, i
 //             <=>  cnt + max(0, b0 - cb * (b0 - b1)) >= full,   b0 = full - half, b1 = full - most   (needs b0 >= 2 * b1)
 // evaluated with a bias of 0x8000 per half so that bit 15 / bit 31 are the two answers and no borrow ever crosses
 // the halves.  Positions are enumerated in increasing cell index (pair, then half), like the scalar sweep.
+// This is rule v2 (acktr/utils.py:8-35), and for footprints of at most 40 cells -- all 16 unrolled ones -- also rule v1
+// (space.py:111-144): count / area > 0.95 then leaves at most one cell below the maximum, so at least three corners sit
+// at it and v1's early "fewer than three corners at the corner maximum" reject cannot fire; otherwise both rules need
+// three or four corners AT THE WINDOW MAXIMUM, which makes the corner maximum equal to it and the two corner counts the
+// same ("v1 vs v2"; the v1 golden masks and the v1 fuzz tests check exactly this path).
 // ---------------------------------------------------------------------------------------------------
 template <int X, int Y, int CS>
 __device__ __forceinline__ int sweep_loop_packed(const uint32_t *pairs, uint8_t *smask, int zmax, int lane)
@@ -603,7 +608,7 @@ __device__ __forceinline__ int sweep_orientation(const uint8_t *tile, uint8_t *s
     const int thr_full = pinned((int)(thr & 1023u)), thr_most = pinned((int)((thr >> 10) & 1023u)),
               thr_half = pinned((int)(thr >> 20));
 #define BPP_SW_CASE(X, Y) case ((X) - 2) * 4 + ((Y) - 2): \
-        if constexpr (kPackedSweep && CS > 0 && VARIANT == 2) return sweep_loop_packed<X, Y, CS>(pairs, smask, zmax, lane); \
+        if constexpr (kPackedSweep && CS > 0 && (VARIANT == 2 || (X) * (Y) <= 40)) return sweep_loop_packed<X, Y, CS>(pairs, smask, zmax, lane); \
         else return sweep_loop<VARIANT, X, Y, CS>(tile, smask, W, x, y, npos, rcp, dW, thr_full, thr_most, thr_half, zmax, lane);
 #define BPP_SW_ROW(X) BPP_SW_CASE(X, 2) BPP_SW_CASE(X, 3) BPP_SW_CASE(X, 4) BPP_SW_CASE(X, 5)
     if (spec) {

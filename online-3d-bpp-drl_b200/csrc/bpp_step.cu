@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kThreads, TMA ? tma_min_blocks(ROT, TMA, CS) :
     const int L = CS ? CS : p.L, W = CS ? CS : p.W, H = p.H, A = CS ? CS * CS : p.A;
     const int A_pad = CS ? ((CS * CS + 15) & ~15) : p.A_pad;
     const int M = A * (ROT ? 2 : 1), M_pad = CS ? ((CS * CS * (ROT ? 2 : 1) + 15) & ~15) : p.M_pad;
-    constexpr bool kPacked = kPackedSweep && CS > 0 && VARIANT == 2;
+    constexpr bool kPacked = kPackedSweep && CS > 0;      // (rule v1 takes the packed loops for the 16 unrolled footprints too)
     // Shared memory.  Without TMA, per warp: heightmap tile | mask tile | pairs; then the 32 staged records per warp.
     // With TMA, per warp: the batch's tiles | mask tile | pairs | f32 staging (heightmap plane, mask row) | records,
     // and once per CTA the table of constant observation planes (values 0 .. CS).

@@ -181,3 +181,26 @@ def test_f32_division_equals_reference_route():
         got_ratio = v.astype(np.float32) / np.float32(lwh)
         assert got_reward.dtype == np.float32 and np.array_equal(got_reward, ref_reward[ok]), lwh
         assert np.array_equal(got_ratio, ref_ratio), lwh
+
+
+def test_rules_v1_and_v2_agree_on_small_footprints():
+    """For footprints of at most 40 cells rule v1 (space.py:111-144) and rule v2 (acktr/utils.py:8-35) give the same verdict --
+    which is why the kernel's packed sweep of the 16 unrolled footprints (sides 2..5) serves both.  Reachable and noisy maps."""
+    import oracle as orc
+    rng = np.random.default_rng(0)
+    for t in range(20000):
+        L = W = 10
+        if t & 1:
+            plain = rng.integers(0, 4, (L, W)).astype(np.int32)
+        else:
+            plain = np.zeros((L, W), np.int32)
+            for _ in range(rng.integers(0, 10)):
+                x, y = rng.integers(1, 7, 2)
+                i, j = rng.integers(0, L - x + 1), rng.integers(0, W - y + 1)
+                plain[i:i + x, j:j + y] = min(10, plain[i:i + x, j:j + y].max() + rng.integers(0, 4))
+        x, y = (rng.integers(2, 6, 2) if t % 3 else rng.integers(1, 9, 2))
+        if x * y > 40:
+            continue
+        z = int(rng.integers(1, 6))
+        lx, ly = rng.integers(0, L - x + 1), rng.integers(0, W - y + 1)
+        assert orc.check_box(plain, x, y, lx, ly, z, (L, W, 10), 1) == orc.check_box(plain, x, y, lx, ly, z, (L, W, 10), 2)
