@@ -111,7 +111,7 @@ const char *bpp_build_info(void)
     return "packed_sweep=" BPP_STR(BPP_PACKED_SWEEP) " lane_check=" BPP_STR(BPP_LANE_CHECK) " square_copy=" BPP_STR(BPP_SQUARE_COPY)
            " plain_stores=" BPP_STR(BPP_PLAIN_STORES) " tma=" BPP_STR(BPP_TMA)
            " tma_bpw_log2=" BPP_STR(BPP_TMA_BPW_LOG2) "/" BPP_STR(BPP_TMA_BPW_LOG2_ROT) " tma20_bpw_log2=" BPP_STR(BPP_TMA20)
-           " warps_per_block=" BPP_STR(BPP_WARPS_PER_BLOCK) " sm_100a";
+           " warps_per_block=" BPP_STR(BPP_WARPS_PER_BLOCK) " (bulk-copy path 10x10: 8 / 7 / 6 by rotation and env count) sm_100a";
 }
 
 int32_t bpp_destroy(bpp_env *env)

@@ -23,7 +23,10 @@ namespace bpp {
 #ifndef BPP_WARPS_PER_BLOCK
 #define BPP_WARPS_PER_BLOCK 8
 #endif
-constexpr int kWarpsPerBlock = BPP_WARPS_PER_BLOCK;
+constexpr int kWarpsPerBlock = BPP_WARPS_PER_BLOCK;      // default CTA size; the 10x10 bulk-copy instantiations pick 6 / 7 / 8 (launch_rv)
+#ifndef BPP_SMALL_CTA_BINS_PER_SM
+#define BPP_SMALL_CTA_BINS_PER_SM 160                  // envs with at least this many bins per SM run the 6-warp CTAs
+#endif
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kMaxSide = 32;          // L, W <= 32 (reciprocal-multiply position decode, smem tile)
 constexpr unsigned kFull = 0xffffffffu;

@@ -50,15 +50,15 @@ inline void derive_params(const bpp_config &cfg, EnvParams &p)
 // Dynamic shared memory of one step-kernel CTA.  Ordinary path: per warp the heightmap tile, the mask tile, the packed
 // sweep's pair array (compile-time bin sides only) and 32 staged bin records.  Bulk-copy path (tma): the table of
 // constant observation planes, then per warp the batch's tiles, mask tile, pairs, float32 staging rows and records.
-inline size_t step_smem_bytes(const EnvParams &p, int tma = 0, int rot = 0)      // tma: log2 of the bins per warp batch, 0 = ordinary path
+inline size_t step_smem_bytes(const EnvParams &p, int tma = 0, int rot = 0, int warps = kWarpsPerBlock)   // tma: log2 of the bins per warp batch, 0 = ordinary path
 {
     const int cs = (p.L == p.W && (p.L == 10 || p.L == 20)) ? p.L : 0;
     if (tma) {
         const int bins = 1 << tma, A = cs * cs, M = A * (rot ? 2 : 1);
         const size_t per_warp = (size_t)bins * ((A + 15) & ~15) + ((M + 15) & ~15) + pair_bytes(cs) + 4 * (size_t)(A + M) + (size_t)bins * 80;
-        return (size_t)tma_lut_planes(cs) * 4 * A + (size_t)kWarpsPerBlock * per_warp;
+        return (size_t)tma_lut_planes(cs) * 4 * A + (size_t)warps * per_warp;
     }
-    return (size_t)kWarpsPerBlock * (size_t)(p.A_pad + p.M_pad + pair_bytes(cs)) + (size_t)kWarpsPerBlock * 32 * 80;
+    return (size_t)warps * (size_t)(p.A_pad + p.M_pad + pair_bytes(cs)) + (size_t)warps * 32 * 80;
 }
 
 }  // namespace bpp

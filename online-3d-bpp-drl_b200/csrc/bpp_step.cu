@@ -31,7 +31,8 @@ constexpr bool kUniformOps = BPP_UNIFORM != 0;
 // (4 with rotation) -- both are built and the launch picks per env size (launch_rv below); at 20x20, 8-bin batches fit 2.
 __host__ __device__ constexpr int tma_min_blocks(int rot, int bpw_log2, int cs = 10)
 {
-    return cs > 10 ? (bpw_log2 >= 4 ? 1 : (bpw_log2 >= 3 || rot ? 2 : 3)) : (bpw_log2 >= 5 ? 3 : (rot ? 4 : 5));
+    return cs > 10 ? (bpw_log2 >= 4 ? 1 : (bpw_log2 >= 3 || rot ? 2 : 3))
+                   : (bpw_log2 >= 5 ? 3 : (rot ? 4 : 5));
 }
 
 namespace bpp {
@@ -93,10 +94,11 @@ __device__ __forceinline__ uint32_t episode_item(const EnvParams &p, long long b
 // Template parameters: ROT = enable_rotation, VARIANT = mask rule, VEC4 = 128-bit output stores possible,
 // CS = compile-time bin side (L == W == CS; 10 and 20 are the reference's configurations, 0 = any size read
 // from EnvParams), FAST = the rollout case (mode == step and every output requested) with the checks folded.
-template <int ROT, int VARIANT, bool VEC4, int CS, bool FAST, int TMA>
-__global__ void __launch_bounds__(kThreads, TMA ? tma_min_blocks(ROT, TMA, CS) : BPP_MIN_BLOCKS) bpp_step_kernel(const EnvParams p, const StepIO io, const int mode_arg)
+template <int ROT, int VARIANT, bool VEC4, int CS, bool FAST, int TMA, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, TMA ? tma_min_blocks(ROT, TMA, CS) : BPP_MIN_BLOCKS) bpp_step_kernel(const EnvParams p, const StepIO io, const int mode_arg)
 {
     static_assert(!TMA || (FAST && VEC4 && CS > 0), "the bulk-copy path is the rollout path of the compile-time bin sizes");
+    constexpr int kWarpsPerBlock = WARPS, kThreads = WARPS * 32;      // (this instantiation's CTA size, see launch_rv)
     const int mode = FAST ? (int)kModeStep : mode_arg;
     const bool w_obs = FAST || io.obs != nullptr, w_mask = FAST || io.mask != nullptr;
     const bool w_sample = io.sample != nullptr || io.packed != nullptr;       // FAST: one of the two is there
@@ -597,14 +599,15 @@ __global__ void __launch_bounds__(kThreads, TMA ? tma_min_blocks(ROT, TMA, CS) :
 }
 
 // One launch: persistent CTAs (one wave of resident blocks, grid-stride over the warp batches).
-template <int ROT, int VARIANT, bool VEC4, int CS, bool FAST, int TMA>
+template <int ROT, int VARIANT, bool VEC4, int CS, bool FAST, int TMA, int WARPS = bpp::kWarpsPerBlock>
 static cudaError_t launch_t(const EnvParams &p, const StepIO &io, int mode, int num_sms, cudaStream_t st)
 {
     // per device and instantiation: resident CTAs per SM for the shared-memory size of the last launch
     static int blocks_per_sm[64] = {0};
     static size_t smem_seen[64] = {0}, smem_opted[64] = {0};
     static std::mutex mu;                                 // two host threads may drive envs on one device
-    const size_t smem = step_smem_bytes(p, TMA, ROT);
+    constexpr int kWarpsPerBlock = WARPS, kThreads = WARPS * 32;
+    const size_t smem = step_smem_bytes(p, TMA, ROT, WARPS);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -614,13 +617,13 @@ static cudaError_t launch_t(const EnvParams &p, const StepIO &io, int mode, int 
         std::lock_guard<std::mutex> lock(mu);
         if (blocks_per_sm[dev] == 0 || smem_seen[dev] != smem) {
             if (smem > 40 * 1024 && smem > smem_opted[dev]) {   // opt in to more than the default dynamic limit
-                e = cudaFuncSetAttribute(bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST, TMA>,
+                e = cudaFuncSetAttribute(bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST, TMA, WARPS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
                 smem_opted[dev] = smem;
             }
             int b = 0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST, TMA>, kThreads, smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST, TMA, WARPS>, kThreads, smem);
             if (e != cudaSuccess) return e;
             blocks_per_sm[dev] = b > 0 ? b : 1;
             smem_seen[dev] = smem;
@@ -664,7 +667,7 @@ static cudaError_t launch_t(const EnvParams &p, const StepIO &io, int mode, int 
     const long long batches = ((long long)p.N + (1 << q.bpw_log2) - 1) >> q.bpw_log2;
     const long long want = (batches + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int grid = (int)(want < cap ? want : cap);
-    BPP_LAUNCH((bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST, TMA>), grid, kThreads, smem, st, q, io, mode);
+    BPP_LAUNCH((bpp_step_kernel<ROT, VARIANT, VEC4, CS, FAST, TMA, WARPS>), grid, kThreads, smem, st, q, io, mode);
     return cudaGetLastError();
 }
 
@@ -675,17 +678,34 @@ static cudaError_t launch_rv(const EnvParams &p, const StepIO &io, int mode, boo
                       ((io.reward && io.counter && io.ratio && io.sample) || io.packed);
     const int cs = (vec4 && p.L == p.W && (p.L == 10 || p.L == 20)) ? p.L : 0;
     if (cs == 10 && fast && kTmaBuild) {
-        // bulk-copy path.  Big envs without rotation: 32-bin batches (3 CTAs per SM) while they still give 80 % of those
-        // warps a batch; otherwise 16-bin batches at 4-5 CTAs per SM (measured: profiles/r2d_ab_trimmed.jsonl).
-        constexpr int kBig = tma_bpw_log2(ROT);
-        const long long warps_big = (long long)num_sms * tma_min_blocks(ROT, kBig) * kWarpsPerBlock;
-        static const char *force = std::getenv("BPP_TMA_FORCE");      // test hook: "5" / "4" picks the instantiation
-        const bool big = force && (force[0] == '4' || force[0] == '5')
-                             ? force[0] == '5'
-                             : (((long long)p.N + (1 << kBig) - 1) >> kBig) >= (warps_big * 4) / 5;
-        if (kBig > 4 && big)
-            return launch_t<ROT, VARIANT, true, 10, true, kBig>(p, io, mode, num_sms, st);
-        return launch_t<ROT, VARIANT, true, 10, true, 4>(p, io, mode, num_sms, st);
+        // Bulk-copy path.  Batch size and CTA size per launch (measured on a B200: profiles/r2d_ab_trimmed.jsonl,
+        // r2l_ab_cta_size.jsonl).  Without rotation: 32-bin batches in 8-warp CTAs (3 per SM) while such batches still give
+        // 80 % of those warps work, else 16-bin batches in 6-warp CTAs.  With rotation (twice the sweep work per bin):
+        // 16-bin batches, in 7-warp CTAs for big envs and 6-warp CTAs for mid-size ones.  The register budget per thread is
+        // the same for every CTA size (tma_min_blocks); the smaller CTAs pack the SM's registers and shared memory with
+        // a different number of warps (the occupancy query in launch_t sizes the grid) and spread a few thousand batches
+        // more evenly over the SMs: -5 % on the rotation headline shape, -5 % on 65 536-bin launches against 8-warp CTAs.
+        static const char *force = std::getenv("BPP_TMA_FORCE");      // test hook: "5" / "4" / "3" picks the big-env / mid-size / small-env instantiation
+        const bool forced = force && force[0] >= '3' && force[0] <= '5';
+        // Below BPP_SMALL_CTA_BINS_PER_SM bins per SM the batch rule of launch_t runs down to a few bins per warp and the
+        // per-CTA setup (the table of constant planes) weighs as much as the packing: 8-warp CTAs stay (4096 bins: 9.0 us
+        // against 9.6 us with 6-warp CTAs; level from 8192 to 24 576; 6-warp CTAs ahead from 32 768 bins,
+        // profiles/r2l_ab_cta_threshold.jsonl).
+        const bool small_ctas = forced ? force[0] == '4' : (long long)p.N >= (long long)num_sms * BPP_SMALL_CTA_BINS_PER_SM;
+        if constexpr (ROT != 0) {
+            const long long warps_big = (long long)num_sms * tma_min_blocks(1, 4) * 7;
+            const bool big = forced ? force[0] == '5' : (((long long)p.N + 15) >> 4) >= warps_big;
+            if (big) return launch_t<ROT, VARIANT, true, 10, true, 4, 7>(p, io, mode, num_sms, st);
+            return small_ctas ? launch_t<ROT, VARIANT, true, 10, true, 4, 6>(p, io, mode, num_sms, st)
+                              : launch_t<ROT, VARIANT, true, 10, true, 4, kWarpsPerBlock>(p, io, mode, num_sms, st);
+        } else {
+            constexpr int kBig = tma_bpw_log2(0);
+            const long long warps_big = (long long)num_sms * tma_min_blocks(0, kBig) * kWarpsPerBlock;
+            const bool big = forced ? force[0] == '5' : (((long long)p.N + (1 << kBig) - 1) >> kBig) >= (warps_big * 4) / 5;
+            if (kBig > 4 && big) return launch_t<ROT, VARIANT, true, 10, true, kBig, kWarpsPerBlock>(p, io, mode, num_sms, st);
+            return small_ctas ? launch_t<ROT, VARIANT, true, 10, true, 4, 6>(p, io, mode, num_sms, st)
+                              : launch_t<ROT, VARIANT, true, 10, true, 4, kWarpsPerBlock>(p, io, mode, num_sms, st);
+        }
     }
     if (cs == 10) return fast ? launch_t<ROT, VARIANT, true, 10, true, 0>(p, io, mode, num_sms, st)
                               : launch_t<ROT, VARIANT, true, 10, false, 0>(p, io, mode, num_sms, st);

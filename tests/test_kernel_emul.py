@@ -281,3 +281,14 @@ def test_bulk_copy_path_32_bin_batches():
     for variant in (2, 1):
         run_against_oracle(1300, (10, 10, 10), False, variant, dict(gen="rs"), T=5, seed=77, edge_every=2, num_sms=2,
                            blocks_per_sm=3)
+
+
+def test_bulk_copy_path_cta_sizes():
+    """The 10x10 bulk-copy instantiations differ in CTA size (launch_rv): 7 warps with rotation once 16-bin batches fill
+    the SMs (1 emulated SM: 28 batches = 433+ bins), 6 warps below that down to 160 bins per SM, 8 warps for smaller envs
+    and for the 32-bin batches above.  Ragged last batch, several batches per warp, fewer CTAs than the kernel was
+    bounded for."""
+    run_against_oracle(470, (10, 10, 10), True, 2, dict(gen="rs"), T=5, seed=78, edge_every=2, num_sms=1, blocks_per_sm=2)
+    run_against_oracle(200, (10, 10, 10), True, 1, dict(gen="rs"), T=5, seed=79, edge_every=2, num_sms=1, blocks_per_sm=2)
+    run_against_oracle(200, (10, 10, 10), False, 2, dict(gen="cut2"), T=6, seed=80, num_sms=1, blocks_per_sm=3)
+    run_against_oracle(150, (10, 10, 10), True, 2, dict(gen="rs"), T=5, seed=81, edge_every=2, num_sms=1, blocks_per_sm=2)

@@ -147,7 +147,10 @@ def main():
         print(json.dumps({"bandwidth": bw}), flush=True)
         del a, b
     for wl in args.workloads:
-        bins, size, rot, gen, desc = bench.WORKLOADS[wl]
+        if ":" in wl:                                   # ad hoc: BINS:ROT, 10x10x10 bins, rs generator
+            bins, size, rot, gen = int(wl.split(":")[0]), (10, 10, 10), wl.split(":")[1] == "1", "rs"
+        else:
+            bins, size, rot, gen, desc = bench.WORKLOADS[wl]
         envs = []
         for name, lib in libs:
             e = Env(lib, bins, size, rot, gen, args.seed, dev)

@@ -7,7 +7,7 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$T.log 2>&1;
 timeout 500 python bench.py --steps 100 --warmup 10 > gpurun_out/bench_$T.json 2> gpurun_out/bench_$T.err; echo "bench exit $?"; tail -2 gpurun_out/bench_$T.err
 timeout 200 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_ref_$T.json 2> gpurun_out/bench_ref_$T.err; echo "ref arm exit $?"
 for tool in memcheck racecheck; do
-  for f in 4 5; do
+  for f in 3 4 5; do
     BPP_TMA_FORCE=$f timeout 240 compute-sanitizer --tool $tool python tools/sanitize_smoke.py > gpurun_out/sanitizer_${tool}_tma${f}_$T.log 2>&1
     echo "$tool tma$f exit $?"; tail -1 gpurun_out/sanitizer_${tool}_tma${f}_$T.log
   done
