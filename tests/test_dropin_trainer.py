@@ -74,7 +74,11 @@ def _train(envs, mask_fn, args, device, updates, kfac, seed):
     rollouts.to(device)
     episodes, losses, valid = 0, [], []
     t0 = time.perf_counter()
-    for _ in range(updates):
+    for u in range(1 + updates):                  # the first update is warm-up (cuBLAS / cuSOLVER handles, lazy module loads)
+        if u == 1:
+            if device.type == "cuda":
+                torch.cuda.synchronize(device)
+            t0 = time.perf_counter()
         for step in range(args.num_steps):
             with torch.no_grad():
                 value, action, action_log_prob, rhs = actor_critic.act(rollouts.obs[step], rollouts.recurrent_hidden_states[step],
@@ -147,7 +151,7 @@ def test_unmodified_acktr_trains_on_the_gpu_env(rot):
                 return obs.to(dev), reward.to(dev), done, infos
         with rl.quiet():
             import tempfile
-            renv = ToDevice(make_vec_envs("Bpp-v0", 1, P, args.gamma, tempfile.mkdtemp(prefix="bpp_ref_log_"), cpu, False, args=args))
+            renv = ToDevice(make_vec_envs("Bpp-v0", 1, P, args.gamma, tempfile.mkdtemp(prefix="bpp_ref_log_"), cpu, True, args=args))   # allow_early_resets: a K-FAC retry resets again
             theirs = train(renv, host_masks, args, dev, updates=4)
             renv.venv.close()
         out["reference_env_stack"] = {"envs": P, "fps": theirs["fps"], "episodes": theirs["episodes"], "optimizer": theirs["optimizer"]}
