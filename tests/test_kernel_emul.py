@@ -292,3 +292,7 @@ def test_bulk_copy_path_cta_sizes():
     run_against_oracle(200, (10, 10, 10), True, 1, dict(gen="rs"), T=5, seed=79, edge_every=2, num_sms=1, blocks_per_sm=2)
     run_against_oracle(200, (10, 10, 10), False, 2, dict(gen="cut2"), T=6, seed=80, num_sms=1, blocks_per_sm=3)
     run_against_oracle(150, (10, 10, 10), True, 2, dict(gen="rs"), T=5, seed=81, edge_every=2, num_sms=1, blocks_per_sm=2)
+    # the remaining (rotation, rule, CTA size) combinations, so that every instantiation of the default build runs
+    run_against_oracle(200, (10, 10, 10), False, 1, dict(gen="rs"), T=4, seed=82, edge_every=2, num_sms=1, blocks_per_sm=2)
+    run_against_oracle(470, (10, 10, 10), True, 1, dict(gen="rs"), T=4, seed=83, edge_every=2, num_sms=1, blocks_per_sm=2)
+    run_against_oracle(200, (10, 10, 10), True, 2, dict(gen="cut1"), T=4, seed=84, num_sms=1, blocks_per_sm=3)
